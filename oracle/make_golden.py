@@ -1,0 +1,199 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference in the build container.
+
+Run from the repo root (the reference tree is read-only, so no bytecode is written):
+
+    PYTHONDONTWRITEBYTECODE=1 python oracle/make_golden.py
+
+* ``stft_wsj0_slice.npz``  -- a slice of the reference's own fixture pair
+  ``data/subset/pickle/CSR-1-WSJ-0/si_et_05_speech-505.p`` -> ``si_et_05_frames.p``
+  (produced by the reference's ``tests/dataset/test_csr1_wjs0_dataset.py:17-83``): the first
+  20 480 samples of utterance 0 after peak normalisation, and the frames of the stored power
+  spectrogram whose analysis windows lie inside that slice.
+* ``mcem_{M1,M2_ibm,M2_vad}.npz`` -- ``/root/reference/python/models/{mcem,models}.py``
+  imported as they are; their module-level ``torch`` name is replaced by a proxy whose
+  ``randn``/``rand`` read a :class:`oracle.mcem_oracle.NoiseTape`, so every random draw is
+  recorded in consumption order.  The reference is driven
+  through its own ``init_parameters`` / ``E_step`` / ``M_step`` /
+  ``compute_expected_neg_log_like`` / ``compute_WF`` (the body of ``EM.run``,
+  ``mcem.py:155-178``), the state after every step is stored, and a second instance is run
+  through ``run()`` itself to check that the stepwise drive is the same computation.
+
+/root/reference does not exist on the GPU box; only the committed .npz files travel.
+"""
+import os
+import pickle
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+REF = "/root/reference"
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "guided-vae-nmf_b200"))
+sys.dont_write_bytecode = True
+
+from oracle import stft_oracle                      # noqa: E402
+from oracle.mcem_oracle import NoiseTape, clean_speech_IBM  # noqa: E402
+from gvn.synth import synth_utterance               # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+STFT_KW = dict(fs=16000, wlen_sec=64e-3, win="hann", hop_percent=0.25, dtype="complex64")
+
+
+class _NumpyOnly(pickle.Unpickler):
+    """The pickles are untrusted input: only numpy reconstruction is allowed."""
+
+    def find_class(self, module, name):
+        if module.split(".")[0] == "numpy":
+            return super().find_class(module, name)
+        raise pickle.UnpicklingError("blocked %s.%s" % (module, name))
+
+
+def _load(name):
+    with open(os.path.join(REF, "data/subset/pickle/CSR-1-WSJ-0", name), "rb") as f:
+        return _NumpyOnly(f).load()
+
+
+def golden_stft():
+    speech = _load("si_et_05_speech-505.p")
+    frames = _load("si_et_05_frames.p")
+    s = speech[0] / np.max(np.abs(speech[0]))        # test_csr1_wjs0_dataset.py:47
+    full = np.abs(stft_oracle.stft(s, **STFT_KW)) ** 2
+    n0 = full.shape[1]
+    err = np.max(np.abs(full - frames[:, :n0])) / np.max(frames[:, :n0])
+    print("stft restatement vs reference fixture (utt 0, %d frames): max err / max = %.2e" % (n0, err))
+    assert err < 1e-6
+    T = 20480
+    keep = (T - 512) // 256 - 1                       # frames untouched by the truncation
+    np.savez_compressed(os.path.join(OUT, "stft_wsj0_slice.npz"),
+                        x=s[:T], power=frames[:, :keep], n_keep=keep,
+                        source="si_et_05_speech-505.p[0]/max -> si_et_05_frames.p[:, :%d]" % keep)
+    # second pin: all three utterances, stored as a per-frame checksum (sum over frequency)
+    col = []
+    for u in speech:
+        u = u / np.max(np.abs(u))
+        col.append((np.abs(stft_oracle.stft(u, **STFT_KW)) ** 2).sum(0))
+    col = np.concatenate(col)
+    ref_col = frames.astype(np.float64).sum(0)
+    print("frame-energy checksum, 3 utterances: max rel err %.2e" % np.max(np.abs(col - ref_col) / ref_col))
+    assert np.max(np.abs(col - ref_col) / ref_col) < 1e-5
+
+
+class _TorchProxy:
+    def __init__(self, tape):
+        self._tape = tape
+
+    def __getattr__(self, name):
+        return getattr(torch, name)
+
+    def randn(self, *shape, **kw):
+        return self._tape.randn(*shape)
+
+    def rand(self, *shape, **kw):
+        return self._tape.rand(*shape)
+
+
+def _reference_modules():
+    sys.path.insert(0, REF)
+    for k in [k for k in sys.modules if k == "python" or k.startswith("python.")]:
+        del sys.modules[k]
+    from python.models import mcem as ref_mcem, models as ref_models
+    sys.path.remove(REF)
+    return ref_mcem, ref_models
+
+
+def _snap(m):
+    return dict(W=m.W.numpy().copy(), H=m.H.numpy().copy(), g=m.g.numpy().copy(),
+                Z=m.Z.numpy().copy(), Vb=m.Vb.numpy().copy())
+
+
+def golden_mcem(tag, model, y_kind, L, K, niter, chain, T=6144, seed=0):
+    ref_mcem, ref_models = _reference_modules()
+    nE, bE, nW, bW = chain
+    x, s, _ = synth_utterance(0, seed=seed, T=T)
+    X = stft_oracle.stft(x, **STFT_KW).T                       # (N,F) as process_utt passes it
+    N, F = X.shape
+    torch.manual_seed(0)
+    if model == "M1":
+        vae = ref_models.VariationalAutoencoder([F, L, [128, 128]])
+        y = None
+    else:
+        y_dim = F if y_kind == "ibm" else 1
+        vae = ref_models.DeepGenerativeModel([F, y_dim, L, [128, 128]], None)
+        if y_kind == "ibm":
+            y = torch.from_numpy(clean_speech_IBM(stft_oracle.stft(s, **STFT_KW), 0.999, 0.999).T.copy())
+        else:
+            g = torch.Generator().manual_seed(5)
+            y = (torch.rand(N, 1, generator=g) > 0.4).float()
+    vae.eval()
+    for p in vae.parameters():
+        p.requires_grad = False
+    # the default Xavier init gives near-flat spectra; perturb the biases so the decoder
+    # output spans a few decades like a trained model would
+    with torch.no_grad():
+        vae.decoder.reconstruction.bias.copy_(torch.linspace(-6.0, -1.0, F))
+        vae.decoder.hidden[0].bias.normal_(0, 0.3)
+        vae.decoder.hidden[1].bias.normal_(0, 0.3)
+
+    def make(tape):
+        ref_mcem.torch = _TorchProxy(tape)
+        cls = ref_mcem.MCEM_M1 if model == "M1" else ref_mcem.MCEM_M2
+        m = cls(niter=niter, nsamples_E_step=nE, burnin_E_step=bE, nsamples_WF=nW,
+                burnin_WF=bW, var_RW=0.01)
+        if model == "M1":
+            m.init_parameters(X=X, vae=vae, nmf_rank=K, eps=1e-8, device="cpu")
+        else:
+            m.init_parameters(X=X, y=y, vae=vae, nmf_rank=K, eps=1e-8, device="cpu")
+        return m
+
+    tape = NoiseTape(seed=1234 + seed)
+    m = make(tape)
+    out = {"init": _snap(m)}
+    cost = []
+    Vs_first = None
+    for n in range(niter):
+        m.E_step()
+        out["E%d" % n] = dict(Z=m.Z.numpy().copy())
+        if n == 0:
+            Vs_first = m.Vs.numpy().copy()
+        m.M_step()
+        cost.append(float(m.compute_expected_neg_log_like()))
+        out["M%d" % n] = _snap(m)
+    WFs, WFn = m.compute_WF(sample=True)
+    S_hat = WFs.numpy() * m.X
+    N_hat = WFn.numpy() * m.X
+    # the same thing through run() itself
+    m2 = make(NoiseTape(draws=tape.draws))
+    cost2 = m2.run()
+    assert np.array_equal(cost2, np.array(cost)), (cost2, cost)
+    assert np.array_equal(m2.S_hat, S_hat) and np.array_equal(m2.N_hat, N_hat)
+    ref_mcem.torch = torch
+
+    draws = tape.draws
+    assert draws[0][0] == "rand" and draws[1][0] == "rand"
+    eps_ = np.stack([t.numpy() for k, t in draws[2:] if k == "randn"])
+    u_ = np.stack([t.numpy() for k, t in draws[2:] if k == "rand"])
+    assert len(eps_) == len(u_)
+    flat = {}
+    for k, d in out.items():
+        for kk, v in d.items():
+            flat["%s_%s" % (k, kk)] = v
+    sd = {"sd_" + k: v.numpy() for k, v in vae.state_dict().items()}
+    np.savez_compressed(
+        os.path.join(OUT, "mcem_%s.npz" % tag),
+        model=model, y_kind=str(y_kind), L=L, K=K, niter=niter, chain=np.array(chain),
+        var_RW=0.01, eps=1e-8, X=X, y=(np.zeros((N, 0), np.float32) if y is None else y.numpy()),
+        rand_W=draws[0][1].numpy(), rand_H=draws[1][1].numpy(), tape_eps=eps_, tape_u=u_,
+        cost=np.array(cost), S_hat=S_hat, N_hat=N_hat, WFs=WFs.numpy(), WFn=WFn.numpy(),
+        Vs_E0=Vs_first, **flat, **sd)
+    print("golden %-7s N=%d L=%d K=%d niter=%d steps=%d cost=%s" % (tag, N, L, K, niter, len(u_), np.round(cost, 4)))
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    golden_stft()
+    golden_mcem("M1", "M1", None, L=16, K=4, niter=2, chain=(3, 4, 2, 5))
+    golden_mcem("M2_ibm", "M2", "ibm", L=16, K=10, niter=3, chain=(3, 5, 4, 6))
+    golden_mcem("M2_vad", "M2", "vad", L=32, K=10, niter=2, chain=(2, 3, 2, 3))

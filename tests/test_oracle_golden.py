@@ -1,0 +1,81 @@
+"""The oracle (oracle/*.py) against the golden vectors produced by the reference itself
+(oracle/make_golden.py) and against the reference's own STFT fixture."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import stft_oracle
+from _util import GOLDEN, load_golden, oracle_from_golden
+
+STFT_KW = dict(fs=16000, wlen_sec=64e-3, win="hann", hop_percent=0.25, dtype="complex64")
+
+
+def test_stft_matches_reference_fixture():
+    z = np.load(os.path.join(GOLDEN, "stft_wsj0_slice.npz"))
+    S = stft_oracle.stft(z["x"], **STFT_KW)
+    assert S.dtype == np.complex64 and S.shape[0] == 513
+    k = int(z["n_keep"])
+    P = np.abs(S[:, :k]) ** 2
+    # the fixture is float32 |.|^2 of a complex64 STFT: allow a few ulp of the frame maximum
+    assert np.max(np.abs(P - z["power"])) <= 2e-6 * np.max(z["power"])
+
+
+@pytest.mark.parametrize("T", [64000, 6144, 20000, 777])
+def test_stft_istft_roundtrip(T):
+    # property of the reference's tests/processing/test_stft.py:10-50 (6 decimals)
+    x = np.random.RandomState(T).randn(T) * 0.1
+    S = stft_oracle.stft(x, **STFT_KW)
+    nfr = 1 + (T + (256 if stft_oracle.needs_end_pad(T, 16000, 64e-3, 0.25) else 0)) // 256
+    assert S.shape == (513, nfr)
+    xh = stft_oracle.istft(S, fs=16000, wlen_sec=64e-3, win="hann", hop_percent=0.25, max_len=T)
+    assert xh.dtype == np.float32 and xh.shape == (T,)
+    np.testing.assert_array_almost_equal(x, xh, decimal=6)
+
+
+def test_stft_rejects_fractional_window():
+    with pytest.raises(ValueError, match="not an integer"):
+        stft_oracle.stft(np.zeros(100), fs=16000, wlen_sec=50.01e-3)
+
+
+@pytest.mark.parametrize("tag", ["M1", "M2_ibm", "M2_vad"])
+def test_oracle_reproduces_reference_run(tag):
+    g = load_golden(tag)
+    o = oracle_from_golden(g)
+    for k in ("W", "H", "g", "Z", "Vb"):
+        np.testing.assert_array_equal(getattr(o, k).numpy(), g["init_" + k], err_msg="init " + k)
+    seen = {}
+
+    def hook(oo, n):
+        seen[n] = {k: getattr(oo, k).numpy().copy() for k in ("W", "H", "g", "Z", "Vb")}
+        if n == 0:
+            seen["Vs0"] = oo.Vs.numpy().copy()
+    o.iter_hook = hook
+    cost = o.run()
+    # same torch ops in the same order on the same draws: bit-for-bit in fp32
+    np.testing.assert_array_equal(cost, g["cost"])
+    for n in range(int(g["niter"])):
+        for k in ("W", "H", "g", "Z", "Vb"):
+            np.testing.assert_array_equal(seen[n][k], g["M%d_%s" % (n, k)], err_msg="iter %d %s" % (n, k))
+    np.testing.assert_array_equal(seen["Vs0"], g["Vs_E0"])
+    np.testing.assert_array_equal(o.S_hat, g["S_hat"])
+    np.testing.assert_array_equal(o.N_hat, g["N_hat"])
+
+
+def test_m1_quirk_chain_lengths():
+    # mcem.py:461-462 / :477-478 shift the positional arguments
+    g = load_golden("M1")
+    o = oracle_from_golden(g)
+    (RE, bE), (RW, bW) = o.chain_lengths()
+    nE, bEc, nW, bWc = [int(v) for v in g["chain"]]
+    assert (RE, bE, RW, bW) == (bEc, 30, bWc, 30)
+    assert g["Vs_E0"].shape[0] == bEc
+    assert len(g["tape_u"]) == int(g["niter"]) * (bEc + 30) + (bWc + 30)
+
+
+def test_oracle_fp64_close_to_fp32():
+    g = load_golden("M2_ibm")
+    o = oracle_from_golden(g, dtype=torch.float64)
+    cost = o.run()
+    np.testing.assert_allclose(cost, g["cost"], rtol=2e-3)
