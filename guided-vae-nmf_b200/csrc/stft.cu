@@ -1,0 +1,162 @@
+// STFT power spectrum and ISTFT, framing / window / |.|^2 / overlap-add fused around a
+// shared-memory radix-2 FFT (n_fft a power of two, <= 4096).
+//
+// Replaces python/processing/stft.py:16-63 and :66-102 of the reference, i.e. the librosa
+// semantics those wrappers select: reflect centring by n_fft/2, periodic Hann, rFFT without
+// scaling; inverse: irFFT * window, overlap-add, division by the overlap-added squared
+// window where it exceeds `tiny`, drop n_fft/2 samples, pad / trim to the requested length.
+#include "gvn_common.cuh"
+
+namespace gvn {
+
+namespace {
+
+constexpr int FFT_THREADS = 256;
+
+__device__ __forceinline__ float hann_periodic(int i, int n) { return 0.5f - 0.5f * cospif(2.0f * (float)i / (float)n); }
+
+__device__ __forceinline__ int bit_reverse(int x, int bits) { return (int)(__brev((unsigned)x) >> (32 - bits)); }
+
+// in-place radix-2 decimation-in-time FFT on bit-reversed input, forward (e^{-i...}) transform
+__device__ void fft_inplace(float2* s, int n, int bits) {
+  for (int st = 1; st <= bits; ++st) {
+    const int half = 1 << (st - 1);
+    for (int idx = threadIdx.x; idx < n / 2; idx += FFT_THREADS) {
+      const int grp = idx >> (st - 1), pos = idx & (half - 1);
+      const int i = (grp << st) + pos, j = i + half;
+      float sn, cs;
+      sincospif(-(float)pos / (float)half, &sn, &cs);
+      const float2 a = s[i], b = s[j];
+      const float2 t = make_float2(cs * b.x - sn * b.y, cs * b.y + sn * b.x);
+      s[i] = make_float2(a.x + t.x, a.y + t.y);
+      s[j] = make_float2(a.x - t.x, a.y - t.y);
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(FFT_THREADS) k_stft_power(int F, int NP, int n_fft, int bits, int hop,
+                                                           const int32_t* __restrict__ frame_utt,
+                                                           const int32_t* __restrict__ frame_off,
+                                                           const float* __restrict__ wav, int T_stride,
+                                                           const int32_t* __restrict__ T, const int32_t* __restrict__ end_pad,
+                                                           float2* __restrict__ Xc, float* __restrict__ X2) {
+  extern __shared__ float2 s_fft[];
+  for (int gn = blockIdx.x; gn < NP; gn += gridDim.x) {
+    const int b = frame_utt[gn];
+    if (b < 0) continue;                       // uniform per CTA
+    const int j = gn - frame_off[b];
+    const int Tb = T[b], Tx = Tb + (end_pad[b] ? hop : 0);
+    const float* x = wav + (size_t)b * T_stride;
+    for (int i = threadIdx.x; i < n_fft; i += FFT_THREADS) {
+      int idx = j * hop + i - n_fft / 2;
+      if (idx < 0) idx = -idx;                 // numpy 'reflect' (no edge repeat)
+      if (idx >= Tx) idx = 2 * (Tx - 1) - idx;
+      float v = (idx >= 0 && idx < Tb) ? x[idx] : 0.f;
+      s_fft[bit_reverse(i, bits)] = make_float2(v * hann_periodic(i, n_fft), 0.f);
+    }
+    __syncthreads();
+    fft_inplace(s_fft, n_fft, bits);
+    for (int f = threadIdx.x; f < F; f += FFT_THREADS) {
+      const float2 v = s_fft[f];
+      const size_t o = (size_t)f * NP + gn;
+      Xc[o] = v;
+      X2[o] = v.x * v.x + v.y * v.y;
+    }
+    __syncthreads();
+  }
+}
+
+// inverse frames: ws[gn][i] = window[i] * irfft(S[:, gn])[i]
+__global__ void __launch_bounds__(FFT_THREADS) k_istft_frames(int F, int NP, int n_fft, int bits,
+                                                             const int32_t* __restrict__ frame_utt,
+                                                             const float2* __restrict__ S, float* __restrict__ ws) {
+  extern __shared__ float2 s_fft[];
+  for (int gn = blockIdx.x; gn < NP; gn += gridDim.x) {
+    if (frame_utt[gn] < 0) continue;
+    // ifft(Y) = conj(fft(conj(Y)))/n with Y the Hermitian extension; the imaginary parts of
+    // the DC and Nyquist bins are ignored, as numpy's irfft does
+    for (int k = threadIdx.x; k < n_fft; k += FFT_THREADS) {
+      float2 v;
+      if (k <= n_fft / 2) {
+        v = S[(size_t)k * NP + gn];
+        v.y = (k == 0 || k == n_fft / 2) ? 0.f : -v.y;      // conj(Y[k])
+      } else {
+        v = S[(size_t)(n_fft - k) * NP + gn];               // conj(conj(S)) = S
+      }
+      s_fft[bit_reverse(k, bits)] = v;
+    }
+    __syncthreads();
+    fft_inplace(s_fft, n_fft, bits);
+    const float inv_n = 1.0f / (float)n_fft;
+    for (int i = threadIdx.x; i < n_fft; i += FFT_THREADS)
+      ws[(size_t)gn * n_fft + i] = s_fft[i].x * inv_n * hann_periodic(i, n_fft);
+    __syncthreads();
+  }
+}
+
+// overlap-add + window-sum-square normalisation, one thread per output sample
+__global__ void k_istft_ola(int n_fft, int hop, int T_stride, const int32_t* __restrict__ frame_off,
+                            const int32_t* __restrict__ n_frames, const int32_t* __restrict__ out_len,
+                            const float* __restrict__ ws, float* __restrict__ out) {
+  const int b = blockIdx.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T_stride) return;
+  float y = 0.f;
+  if (t < out_len[b]) {
+    const int pos = t + n_fft / 2, N = n_frames[b], off = frame_off[b];
+    int j_lo = pos - n_fft + 1;
+    j_lo = j_lo <= 0 ? 0 : (j_lo + hop - 1) / hop;
+    int j_hi = pos / hop;
+    if (j_hi > N - 1) j_hi = N - 1;
+    float wss = 0.f;
+    for (int j = j_lo; j <= j_hi; ++j) {
+      const int i = pos - j * hop;
+      const float w = hann_periodic(i, n_fft);
+      y += ws[(size_t)(off + j) * n_fft + i];
+      wss = fmaf(w, w, wss);
+    }
+    if (wss > 1.1754944e-38f) y /= wss;
+  }
+  out[(size_t)b * T_stride + t] = y;
+}
+
+int log2_exact(int n) {
+  int b = 0;
+  while ((1 << b) < n) ++b;
+  return (1 << b) == n ? b : -1;
+}
+
+}  // namespace
+
+int32_t launch_stft_power(const gvn_batch* b, const float* wav, int T_stride, const int32_t* T, const int32_t* end_pad,
+                          int n_fft, int hop, cudaStream_t st) {
+  int bits = log2_exact(n_fft);
+  GVN_REQUIRE(bits >= 4 && bits <= 12, GVN_E_UNSUPPORTED_SHAPE, "n_fft=%d must be a power of two in [16,4096]", n_fft);
+  GVN_REQUIRE(b->F == n_fft / 2 + 1, GVN_E_INVALID, "F=%d does not match n_fft=%d", b->F, n_fft);
+  int grid = b->NP < 148 * 8 ? b->NP : 148 * 8;
+  k_stft_power<<<grid, FFT_THREADS, (size_t)n_fft * sizeof(float2), st>>>(
+      b->F, b->NP, n_fft, bits, hop, b->frame_utt, b->frame_off, wav, T_stride, T, end_pad,
+      reinterpret_cast<float2*>(b->Xc), b->X2);
+  return check_launch("k_stft_power");
+}
+
+size_t istft_workspace_bytes(const gvn_batch* b, int n_fft) { return (size_t)b->NP * n_fft * sizeof(float); }
+
+int32_t launch_istft(const gvn_batch* b, const float* S, int n_fft, int hop, const int32_t* out_len, float* out,
+                     int T_stride, void* workspace, cudaStream_t st) {
+  int bits = log2_exact(n_fft);
+  GVN_REQUIRE(bits >= 4 && bits <= 12, GVN_E_UNSUPPORTED_SHAPE, "n_fft=%d must be a power of two in [16,4096]", n_fft);
+  GVN_REQUIRE(b->F == n_fft / 2 + 1, GVN_E_INVALID, "F=%d does not match n_fft=%d", b->F, n_fft);
+  float* ws = reinterpret_cast<float*>(workspace);
+  int grid = b->NP < 148 * 8 ? b->NP : 148 * 8;
+  k_istft_frames<<<grid, FFT_THREADS, (size_t)n_fft * sizeof(float2), st>>>(b->F, b->NP, n_fft, bits, b->frame_utt,
+                                                                           reinterpret_cast<const float2*>(S), ws);
+  int32_t rc = check_launch("k_istft_frames");
+  if (rc) return rc;
+  dim3 g2((T_stride + 255) / 256, b->B);
+  k_istft_ola<<<g2, 256, 0, st>>>(n_fft, hop, T_stride, b->frame_off, b->n_frames, out_len, ws, out);
+  return check_launch("k_istft_ola");
+}
+
+}  // namespace gvn

@@ -1,0 +1,390 @@
+"""Host side of the hot path: batch state in HBM and the calls into libgvn.so.
+
+PyTorch is used for device memory, streams and host<->device copies only; every arithmetic
+step of the path (STFT, encoder/classifier layers, MH chains, NMF updates, Wiener filter,
+ISTFT) is a kernel of libgvn.so reached through the C ABI in include/gvn.h.
+
+The unit of work is a *batch* of utterances laid side by side on one padded global frame
+axis (see include/gvn.h).  The reference API (one utterance per ``init_parameters``/``run``,
+python/models/mcem.py:155-178, :207-216) is the B=1 view provided by ``python/models/mcem.py``
+in this package.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import GvnBatch, GvnNoise, GvnTrace, GVN_FRAME_ALIGN, GVN_HIDDEN, PRECISIONS, check
+
+
+def _ptr(t):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _require_cuda(device):
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError("gvn: the MCEM hot path runs on CUDA (sm_100a) only; got device %r. "
+                           "There is no CPU fallback." % (device,))
+    return device
+
+
+# --------------------------------------------------------------------------------------
+# decoder / encoder / classifier weights
+# --------------------------------------------------------------------------------------
+def latent_dim(vae):
+    """mcem.py:224-227 -- `latent_dim` first, then `z_dim`."""
+    if hasattr(vae, "latent_dim"):
+        return int(vae.latent_dim)
+    return int(vae.z_dim)
+
+
+class PackedDecoder:
+    """Decoder weights (models.py:107-121) repacked once per model for the kernels."""
+
+    def __init__(self, vae, device):
+        if type(vae).__name__ == "RVAE":                        # mcem.py:208-209 / :362-363
+            raise NameError("MCEM algorithm only valid for FFNN VAE")
+        device = _require_cuda(device)
+        lib = _lib.load()
+        dec = vae.decoder
+        if len(dec.hidden) != 2:
+            raise _lib.GvnError(_lib.E_UNSUPPORTED_SHAPE, "decoder must have two hidden layers")
+        f32 = dict(device=device, dtype=torch.float32)
+        w = [dec.hidden[0].weight, dec.hidden[0].bias, dec.hidden[1].weight, dec.hidden[1].bias,
+             dec.reconstruction.weight, dec.reconstruction.bias]
+        w = [t.detach().to(**f32).contiguous() for t in w]
+        self.L = latent_dim(vae)
+        self.hidden = w[0].shape[0]
+        self.y_dim = w[0].shape[1] - self.L
+        self.F = w[4].shape[0]
+        self.device = device
+        nbytes = lib.gvn_decoder_packed_bytes(self.L, self.y_dim, self.F, self.hidden)
+        if nbytes == 0:
+            raise _lib.GvnError(_lib.E_UNSUPPORTED_SHAPE,
+                                "unsupported decoder shape L=%d y_dim=%d F=%d hidden=%d (hidden must be %d, L<=%d)"
+                                % (self.L, self.y_dim, self.F, self.hidden, GVN_HIDDEN, _lib.GVN_MAX_L))
+        self.packed = torch.zeros(nbytes, dtype=torch.uint8, device=device)
+        with torch.cuda.device(device):
+            check(lib.gvn_pack_decoder(*[_ptr(t) for t in w], self.L, self.y_dim, self.F, self.hidden,
+                                       _ptr(self.packed), _stream()))
+        self._keep = w
+
+
+def _linear_params(layer, device):
+    return (layer.weight.detach().to(device=device, dtype=torch.float32).contiguous(),
+            layer.bias.detach().to(device=device, dtype=torch.float32).contiguous())
+
+
+def dense(W, b, in0, in1, act, NP, mean=None, std=None, eps=0.0):
+    """out[j][n] = act(b[j] + sum_i W[j][i] [in0;in1][i][n]) on feature-major activations."""
+    lib = _lib.load()
+    D0 = 0 if in0 is None else in0.shape[0]
+    D1 = 0 if in1 is None else in1.shape[0]
+    assert W.shape[1] == D0 + D1, (W.shape, D0, D1)
+    out = torch.empty(W.shape[0], NP, dtype=torch.float32, device=W.device)
+    acts = {"none": 0, "tanh": 1, "relu": 2, "sigmoid": 3, "hard": 4}
+    check(lib.gvn_dense(_ptr(W), _ptr(b), _ptr(in0), D0, _ptr(in1), D1, _ptr(mean), _ptr(std), float(eps),
+                        W.shape[0], NP, acts[act], _ptr(out), _stream()))
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# batch state
+# --------------------------------------------------------------------------------------
+class Batch:
+    """Device state of B utterances (layout documented in include/gvn.h)."""
+
+    def __init__(self, n_frames, F, K, L, R_cap, device, with_complex=True):
+        device = _require_cuda(device)
+        self.device = device
+        n_frames = [int(n) for n in n_frames]
+        assert len(n_frames) > 0 and min(n_frames) > 0
+        self.B, self.F, self.K, self.L, self.R_cap = len(n_frames), int(F), int(K), int(L), int(R_cap)
+        A = GVN_FRAME_ALIGN
+        off = [0]
+        for n in n_frames:
+            off.append(off[-1] + (n + A - 1) // A * A)
+        self.NP = off[-1]
+        self.n_frames_host = n_frames
+        self.frame_off_host = off
+        utt = np.full(self.NP, -1, np.int32)
+        for b, n in enumerate(n_frames):
+            utt[off[b]:off[b] + n] = b
+        i32 = dict(dtype=torch.int32, device=device)
+        self.frame_off = torch.tensor(off, **i32)
+        self.n_frames = torch.tensor(n_frames, **i32)
+        self.frame_utt = torch.from_numpy(utt).to(device)
+        f32 = dict(dtype=torch.float32, device=device)
+        NP = self.NP
+        self.X2 = torch.ones(F, NP, **f32)
+        self.Xc = torch.zeros(F, NP, 2, **f32) if with_complex else None
+        self.W = torch.empty(self.B, F, K, **f32)
+        self.Wun = torch.empty(self.B, F, K, **f32)
+        self.H = torch.ones(K, NP, **f32)
+        self.g = torch.ones(NP, **f32)
+        self.Vb = torch.ones(F, NP, **f32)
+        self.Z = torch.zeros(L, NP, **f32)
+        self.Vs = torch.empty(R_cap, F, NP, **f32)
+        self.yproj = torch.zeros(GVN_HIDDEN, NP, **f32)
+        self.y = None
+        self._struct = None
+
+    def struct(self):
+        s = GvnBatch()
+        s.B, s.F, s.K, s.L, s.NP, s.R_cap = self.B, self.F, self.K, self.L, self.NP, self.R_cap
+        for name in ("frame_off", "n_frames", "frame_utt", "X2", "Xc", "W", "Wun", "H", "g", "Vb", "Z", "Vs", "yproj"):
+            t = getattr(self, name)
+            setattr(s, name, 0 if t is None else t.data_ptr())
+        self._struct = s
+        return C.byref(s)
+
+    # ---- scatter / gather between per-utterance arrays and the global frame axis ----
+    def cols(self, b):
+        o = self.frame_off_host[b]
+        return slice(o, o + self.n_frames_host[b])
+
+    def scatter_cols(self, dst, per_utt):
+        """dst[..., NP]  <-  list of [..., N_b] tensors (host or device)."""
+        for b, t in enumerate(per_utt):
+            dst[..., self.cols(b)] = torch.as_tensor(t).to(device=dst.device, dtype=dst.dtype)
+
+    def gather_cols(self, src, b):
+        return src[..., self.cols(b)]
+
+
+# --------------------------------------------------------------------------------------
+# STFT / ISTFT (python/processing/stft.py)
+# --------------------------------------------------------------------------------------
+def stft_geometry(T, fs, wlen_sec, hop_percent):
+    """Window, hop, end-pad flag and frame count for a signal of T samples (stft.py:37-53)."""
+    if wlen_sec * fs != int(wlen_sec * fs):
+        raise ValueError("wlen_sample of STFT is not an integer.")
+    nfft = int(wlen_sec * fs)
+    hop = int(hop_percent * nfft)
+    q = (T / fs) / wlen_sec / hop_percent
+    end_pad = math.ceil(q) != int(q)
+    Tx = T + (hop if end_pad else 0)
+    return nfft, hop, end_pad, 1 + Tx // hop
+
+
+def upload_waveforms(wavs, device, pinned=None):
+    """Packs B waveforms into one zero-padded (B, T_stride) f32 tensor on the device."""
+    B = len(wavs)
+    T = [len(w) for w in wavs]
+    T_stride = (max(T) + 3) // 4 * 4
+    host = pinned if pinned is not None else torch.zeros(B, T_stride, dtype=torch.float32).pin_memory()
+    for b, w in enumerate(wavs):
+        host[b, :T[b]] = torch.as_tensor(np.asarray(w, dtype=np.float32))
+        host[b, T[b]:] = 0
+    return host.to(device, non_blocking=True), T, T_stride
+
+
+def stft_into(batch, wav_dev, T, T_stride, n_fft, hop, end_pad):
+    lib = _lib.load()
+    i32 = dict(dtype=torch.int32, device=batch.device)
+    T_d = torch.tensor(T, **i32)
+    ep_d = torch.tensor([int(e) for e in end_pad], **i32)
+    if min(T) <= n_fft // 2:
+        raise _lib.GvnError(_lib.E_INVALID, "signal shorter than n_fft/2 cannot be reflect-padded")
+    check(lib.gvn_stft_power(batch.struct(), _ptr(wav_dev), T_stride, _ptr(T_d), _ptr(ep_d), n_fft, hop, _stream()))
+    return T_d, ep_d
+
+
+def istft_from(batch, S, out_len, T_stride, n_fft, hop):
+    """S: [F][NP][2] f32 on device -> (B, T_stride) f32 waveforms on device."""
+    lib = _lib.load()
+    ol = torch.tensor([int(v) for v in out_len], dtype=torch.int32, device=batch.device)
+    out = torch.empty(batch.B, T_stride, dtype=torch.float32, device=batch.device)
+    ws = torch.empty(lib.gvn_istft_workspace_bytes(batch.struct(), n_fft), dtype=torch.uint8, device=batch.device)
+    check(lib.gvn_istft(batch.struct(), _ptr(S), n_fft, hop, _ptr(ol), _ptr(out), T_stride, _ptr(ws), _stream()))
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# per-utterance initialisation (mcem.py:36-57, :207-216, :361-369)
+# --------------------------------------------------------------------------------------
+def init_nmf(batch, eps, rand_W=None, rand_H=None, generator=None):
+    """W = max(rand(F,K), eps), H = max(rand(K,N), eps), g = 1, Vb = W@H  (mcem.py:41-51)."""
+    lib = _lib.load()
+    f32 = dict(dtype=torch.float32, device=batch.device)
+    if rand_W is None:
+        rand_W = torch.rand(batch.B, batch.F, batch.K, generator=generator, **f32)
+        rand_H = torch.rand(batch.K, batch.NP, generator=generator, **f32)
+    else:
+        rw = torch.stack([torch.as_tensor(w) for w in rand_W]).to(**f32)
+        rh = torch.ones(batch.K, batch.NP, **f32)
+        batch.scatter_cols(rh, rand_H)
+        rand_W, rand_H = rw.contiguous(), rh
+    check(lib.gvn_init_nmf(batch.struct(), _ptr(rand_W), _ptr(rand_H), float(eps), _stream()))
+
+
+def set_labels(batch, dec, y):
+    """y: None (M1) or [y_dim][NP] device tensor.  Computes yproj (label half of layer 1)."""
+    lib = _lib.load()
+    batch.y = y
+    check(lib.gvn_label_projection(_ptr(dec.packed), _ptr(y), dec.L, dec.y_dim, dec.F, batch.NP,
+                                   _ptr(batch.yproj), _stream()))
+
+
+def encode_init(batch, vae):
+    """Z <- encoder mean of [X2; y]  (mcem.py:214-215 / :367-368; models.py:90-104)."""
+    enc = vae.encoder
+    x, y = batch.X2, batch.y
+    h = None
+    for i, layer in enumerate(enc.hidden):
+        W, b = _linear_params(layer, batch.device)
+        h = dense(W, b, x, y, "tanh", batch.NP) if i == 0 else dense(W, b, h, None, "tanh", batch.NP)
+    W, b = _linear_params(enc.sample.mu, batch.device)
+    batch.Z.copy_(dense(W, b, h, None, "none", batch.NP))
+
+
+def classify(batch, classifier, mean=None, std=None, eps=0.0, hard=True):
+    """Guide label from the supervised classifier (models.py:41-62 with the standardisation
+    of scripts/evaluate_M2_ibm.py:121-130).  Returns [y_dim][NP] on the device."""
+    h = None
+    for i, layer in enumerate(classifier.hidden):
+        W, b = _linear_params(layer, batch.device)
+        if i == 0:
+            m = None if mean is None else torch.as_tensor(mean, dtype=torch.float32, device=batch.device).reshape(-1).contiguous()
+            s = None if std is None else torch.as_tensor(std, dtype=torch.float32, device=batch.device).reshape(-1).contiguous()
+            h = dense(W, b, batch.X2, None, "relu", batch.NP, m, s, eps)
+        else:
+            h = dense(W, b, h, None, "relu", batch.NP)
+    W, b = _linear_params(classifier.output_layer, batch.device)
+    return dense(W, b, h, None, "hard" if hard else "sigmoid", batch.NP)
+
+
+# --------------------------------------------------------------------------------------
+# the MCEM loop (mcem.py:155-178)
+# --------------------------------------------------------------------------------------
+class ReplayNoise:
+    """Recorded draws for parity runs: a list over chains of (eps [steps][L][NP], u [steps][NP])."""
+
+    def __init__(self, chains, forced=None):
+        self.chains = chains
+        self.forced = forced
+
+    @staticmethod
+    def from_utterance_tapes(batch, tapes_eps, tapes_u, chain_steps):
+        """tapes_eps[b]: (total_steps, L, N_b), tapes_u[b]: (total_steps, N_b); split into chains."""
+        chains, s0 = [], 0
+        f32 = dict(dtype=torch.float32, device=batch.device)
+        for steps in chain_steps:
+            e = torch.zeros(steps, batch.L, batch.NP, **f32)
+            u = torch.full((steps, batch.NP), 0.5, **f32)
+            batch.scatter_cols(e, [t[s0:s0 + steps] for t in tapes_eps])
+            batch.scatter_cols(u, [t[s0:s0 + steps] for t in tapes_u])
+            chains.append((e.contiguous(), u.contiguous()))
+            s0 += steps
+        return ReplayNoise(chains)
+
+
+def estep(batch, dec, burnin, R, var_RW, precision="fp32", seed=0, chain=0, eps=None, u=None, forced=None,
+          trace=False):
+    """One MH chain over all frames (gvn_estep).  Returns the trace tensors if requested."""
+    lib = _lib.load()
+    nz = GvnNoise()
+    nz.eps, nz.u = (0 if eps is None else eps.data_ptr()), (0 if u is None else u.data_ptr())
+    nz.forced_accept = 0 if forced is None else forced.data_ptr()
+    nz.seed, nz.chain = int(seed) & (2 ** 64 - 1), int(chain)
+    tr, out = None, None
+    if trace:
+        steps = burnin + R
+        acc = torch.zeros(steps, batch.NP, dtype=torch.float32, device=batch.device)
+        dec_ = torch.zeros(steps, batch.NP, dtype=torch.uint8, device=batch.device)
+        cnt = torch.zeros(batch.NP, dtype=torch.int32, device=batch.device)
+        zs = torch.zeros(R, batch.L, batch.NP, dtype=torch.float32, device=batch.device)
+        tr = GvnTrace()
+        tr.acc_prob, tr.accepted, tr.n_accepted = acc.data_ptr(), dec_.data_ptr(), cnt.data_ptr()
+        tr.z_samples = zs.data_ptr()
+        out = (acc, dec_, cnt, zs)
+    check(lib.gvn_estep(batch.struct(), _ptr(dec.packed), int(burnin), int(R), float(np.float32(var_RW)),
+                        C.byref(nz), C.byref(tr) if tr is not None else None, PRECISIONS[precision], _stream()))
+    return out
+
+
+class MstepScratch:
+    def __init__(self, batch, niter):
+        lib = _lib.load()
+        self.ws = torch.empty(max(16, lib.gvn_mstep_workspace_bytes(batch.struct())), dtype=torch.uint8, device=batch.device)
+        self.ntiles = batch.NP // GVN_FRAME_ALIGN
+        self.cost_part = torch.zeros(niter, self.ntiles, dtype=torch.float32, device=batch.device)
+
+
+def mstep(batch, R, scratch, it, variant=0):
+    lib = _lib.load()
+    check(lib.gvn_mstep(batch.struct(), int(R), _ptr(scratch.cost_part[it]), _ptr(scratch.ws), int(variant), _stream()))
+
+
+def cost_reduce(batch, R, scratch, niter):
+    lib = _lib.load()
+    cost = torch.empty(niter, batch.B, dtype=torch.float64, device=batch.device)
+    check(lib.gvn_cost_reduce(batch.struct(), int(R), int(niter), _ptr(scratch.cost_part), _ptr(cost), _stream()))
+    return cost
+
+
+def wiener(batch, R, want_masks=False):
+    lib = _lib.load()
+    f32 = dict(dtype=torch.float32, device=batch.device)
+    S = torch.empty(batch.F, batch.NP, 2, **f32)
+    Nn = torch.empty(batch.F, batch.NP, 2, **f32)
+    WFs = torch.empty(batch.F, batch.NP, **f32) if want_masks else None
+    WFn = torch.empty(batch.F, batch.NP, **f32) if want_masks else None
+    check(lib.gvn_wiener(batch.struct(), int(R), _ptr(S), _ptr(Nn), _ptr(WFs), _ptr(WFn), _stream()))
+    return S, Nn, WFs, WFn
+
+
+class KernelTimers:
+    """CUDA-event brackets around the E-step and M-step launches of a run (for the roofline
+    figures of bench.py).  Events are recorded on the launching stream; read after a sync."""
+
+    def __init__(self):
+        self.spans = {"estep": [], "mstep": []}
+        self.launches = 0
+
+    def bracket(self, kind):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.spans[kind].append((a, b))
+        return a, b
+
+    def total_ms(self, kind):
+        return sum(a.elapsed_time(b) for a, b in self.spans[kind])
+
+    def count(self, kind):
+        return len(self.spans[kind])
+
+
+def run_mcem(batch, dec, niter, chain_E, chain_WF, var_RW, precision="fp32", seed=0, noise=None,
+             mstep_variant=0, want_masks=False, iter_hook=None, timers=None):
+    """EM.run (mcem.py:155-178) for the whole batch: niter x (E-step chain, M-step), then the
+    Wiener chain.  chain_E / chain_WF are (R, burnin).  Returns (cost[niter][B] f64 device
+    tensor, S_hat, N_hat, WFs, WFn).  Nothing here synchronises the host."""
+    (R_E, b_E), (R_W, b_W) = chain_E, chain_WF
+    assert max(R_E, R_W) <= batch.R_cap
+    scratch = MstepScratch(batch, niter)
+    def timed(kind, fn, *a):
+        if timers is None:
+            return fn(*a)
+        t0, t1 = timers.bracket(kind)
+        t0.record()
+        fn(*a)
+        t1.record()
+
+    for n in range(niter):
+        e, u = (noise.chains[n] if noise is not None else (None, None))
+        timed("estep", estep, batch, dec, b_E, R_E, var_RW, precision, seed, n, e, u)
+        timed("mstep", mstep, batch, R_E, scratch, n, mstep_variant)
+        if iter_hook is not None:
+            iter_hook(batch, n)
+    e, u = (noise.chains[niter] if noise is not None else (None, None))
+    timed("estep", estep, batch, dec, b_W, R_W, var_RW, precision, seed, niter, e, u)
+    cost = cost_reduce(batch, R_E, scratch, niter)
+    S, Nn, WFs, WFn = wiener(batch, R_W, want_masks)
+    return cost, S, Nn, WFs, WFn
