@@ -87,7 +87,9 @@ def test_forced_decision_run_matches_golden(tag):
         np.testing.assert_allclose(m.Vs.cpu().numpy(), snaps[n]["Vs"], rtol=RTOL, err_msg="Vs iter %d" % n)
         m.M_step()
         for k in ("W", "H", "g", "Vb", "Z"):
-            np.testing.assert_allclose(getattr(m, k).cpu().numpy(), g["M%d_%s" % (n, k)], rtol=RTOL, atol=1e-7,
+            # Z is a sum of O(1) increments: its entries near zero carry an absolute error
+            atol = 2e-6 if k == "Z" else 1e-7
+            np.testing.assert_allclose(getattr(m, k).cpu().numpy(), g["M%d_%s" % (n, k)], rtol=RTOL, atol=atol,
                                        err_msg="%s iter %d" % (k, n))
         c = float(m.compute_expected_neg_log_like())
         assert abs(c - g["cost"][n]) <= RTOL * abs(g["cost"][n])
