@@ -1,0 +1,39 @@
+"""Utterance-level data parallelism (the only parallelism of the path).
+
+The reference splits its file list with ``np.array_split(file_paths, nb_devices)`` and starts one
+process per GPU (scripts/evaluate_M1.py:203-216); results leave the workers as files.  Here the
+split is the same (contiguous shards, the first ``n % world`` ranks get one extra utterance) and
+the per-utterance result rows are brought together with one all-gather (NCCL on GPUs, gloo in
+the CPU tests).  Nothing else is communicated: utterances are independent problems.
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n, world, rank):
+    """[start, stop) of rank's contiguous shard, np.array_split semantics."""
+    base, extra = divmod(n, world)
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+def shard_list(items, world, rank):
+    a, b = shard_bounds(len(items), world, rank)
+    return items[a:b]
+
+
+def gather_rows(rows, n_total, world=None, rank=None):
+    """rows: (n_local, C) tensor of this rank's result rows (first column = utterance id).
+    Returns the (n_total, C) table ordered by utterance id on every rank."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return rows
+    world = dist.get_world_size() if world is None else world
+    rank = dist.get_rank() if rank is None else rank
+    cap = max(shard_bounds(n_total, world, r)[1] - shard_bounds(n_total, world, r)[0] for r in range(world))
+    pad = torch.full((cap, rows.shape[1]), -1.0, dtype=rows.dtype, device=rows.device)
+    pad[:rows.shape[0]] = rows
+    out = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(out, pad)
+    table = torch.cat(out, 0)
+    table = table[table[:, 0] >= 0]
+    return table[torch.argsort(table[:, 0])]

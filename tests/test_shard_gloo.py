@@ -1,0 +1,52 @@
+"""The N>1 host logic on CPU: utterance sharding and the result gather, world_size 2, gloo."""
+import os
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from gvn.shard import shard_bounds, shard_list, gather_rows
+
+
+def test_shard_bounds_match_array_split():
+    # scripts/evaluate_M1.py:203 uses np.array_split(file_paths, nb_devices)
+    for n in (0, 1, 7, 64, 513, 1000):
+        for world in (1, 2, 3, 8):
+            ref = np.array_split(np.arange(n), world)
+            for r in range(world):
+                a, b = shard_bounds(n, world, r)
+                assert list(range(a, b)) == list(ref[r])
+    assert shard_list(list("abcde"), 2, 0) == ["a", "b", "c"] and shard_list(list("abcde"), 2, 1) == ["d", "e"]
+
+
+def _worker(rank, world, port, n_total, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    a, b = shard_bounds(n_total, world, rank)
+    ids = torch.arange(a, b, dtype=torch.float64)
+    rows = torch.stack([ids, ids * 10 + rank], 1)
+    table = gather_rows(rows, n_total)
+    q.put((rank, table.numpy()))
+    dist.destroy_process_group()
+
+
+def test_gather_rows_world2_gloo():
+    world, n_total = 2, 7                       # ragged: shards of 4 and 3
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 500
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_total, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for r in range(world):
+        t = res[r]
+        assert t.shape == (n_total, 2)
+        np.testing.assert_array_equal(t[:, 0], np.arange(n_total))
+        owner = np.array([0, 0, 0, 0, 1, 1, 1])
+        np.testing.assert_array_equal(t[:, 1], np.arange(n_total) * 10 + owner)
