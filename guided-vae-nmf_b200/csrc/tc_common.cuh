@@ -1,0 +1,141 @@
+// Inline-PTX wrappers for the Blackwell (sm_100a) tensor-core path: tcgen05.mma with
+// accumulators and the A operand in TMEM, B operand in shared memory (canonical no-swizzle
+// K-major layout), mbarriers, TMA.  Bit layouts follow the PTX ISA "tcgen05" chapter; they
+// were cross-checked against the CUTLASS headers vendored in this image
+// (cute/arch/mma_sm100_desc.hpp: SmemDescriptor / InstrDescriptor) and verified on hardware
+// by gvn_selftest_umma (tests/test_gpu_tc.py).
+#pragma once
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+namespace gvn {
+namespace tc {
+
+// ---- shared-memory matrix descriptor (64 bit) ------------------------------------------------
+//  [0,14)  start address >> 4      [16,30) leading-dim byte offset >> 4
+//  [32,46) stride-dim byte offset >> 4   [46,48) version = 1 on sm_100   [61,64) swizzle (0 = none)
+// Canonical K-major no-swizzle layout, in 16-byte units: ((8,n),2):((1,SBO),LBO) -- a core matrix is
+// 8 rows x 16 bytes stored contiguously (128 B); LBO = distance between the two K-halves of one
+// MMA (K=16 f16 = 2 x 16 B), SBO = distance between consecutive 8-row groups.
+__host__ __device__ inline uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+
+// ---- instruction descriptor (32 bit) for kind::f16, f16 x f16 -> f32, both operands K-major ---
+//  [4,6) D format (1 = f32)  [7,10) A format (0 = f16)  [10,13) B format (0 = f16)
+//  [15] A major (0 = K)  [16] B major (0 = K)  [17,23) N >> 3  [24,29) M >> 4
+__host__ __device__ inline uint32_t idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// byte offset of element (n, k) of an [N][K] f16 matrix inside its packed image:
+// 8x8 core matrices (128 B), K-chunks innermost, then 8-row groups.  K multiple of 8.
+__host__ __device__ inline size_t img_offset(int n, int k, int K) {
+  return ((size_t)(n >> 3) * (K >> 3) + (k >> 3)) * 128 + (size_t)(n & 7) * 16 + (size_t)(k & 7) * 2;
+}
+// descriptor strides of such an image
+__host__ __device__ inline uint32_t img_lbo() { return 128; }
+__host__ __device__ inline uint32_t img_sbo(int K) { return (uint32_t)(K >> 3) * 128; }
+
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- TMEM allocation (one full warp) ----
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot_in_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_in_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- MMA: D[tmem] (+)= A[tmem] * B[smem]^T, issued by ONE thread ----
+__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// completion of all MMAs issued so far by this thread -> one arrival on an mbarrier
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// ---- TMEM <-> registers, 32 lanes x 32 bit, N consecutive columns per thread ----
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                 "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// ---- mbarrier ----
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// Bounded spin: a wait that cannot complete traps instead of hanging the GPU (a protocol bug
+// must surface as a launch error, never as a stuck device).
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  for (uint32_t spins = 0; !ok; ++spins) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    if (spins > (1u << 26)) __trap();
+  }
+}
+
+// ---- TMA: 2-D tiled load global -> shared, completion on an mbarrier ----
+__device__ __forceinline__ void tma_load_2d(void* dst_smem, const void* tmap, int x, int y, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(dst_smem)),
+               "l"(tmap), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
+}
+// 1-D bulk copy global -> shared (no tensor map), completion on an mbarrier
+__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// f32 pair -> packed f16x2 with `lo` in bits [0,16)
+__device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
+  __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+#endif  // __CUDACC__
+
+}  // namespace tc
+}  // namespace gvn

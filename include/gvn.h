@@ -169,6 +169,12 @@ int32_t gvn_dense(const float* W, const float* b, const float* in0, int32_t D0, 
 int32_t gvn_init_nmf(const gvn_batch* batch /*HOST*/, const float* rand_W /*[B][F][K]*/,
                      const float* rand_H /*[K][NP]*/, float eps, void* stream);
 
+/* Hardware self test of the tensor-core plumbing used by gvn_estep in the f16 modes:
+ * D[128][N] = A[128][K] @ W[N][K]^T through tcgen05.st (A -> TMEM), a packed shared-memory
+ * image of W, tcgen05.mma and tcgen05.ld.  variant bit2 selects the 3-term hi/lo split. */
+int32_t gvn_selftest_umma(const float* A, const float* W, int32_t N, int32_t K, int32_t variant,
+                          float* D, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

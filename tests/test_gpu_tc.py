@@ -1,0 +1,95 @@
+"""Tensor-core (tcgen05/TMEM) E-step: hardware self test of the UMMA plumbing and parity of the
+f16 chain against the fp32 CUDA-core chain and the oracle.  f16 operands carry 11 mantissa bits
+(= TF32), so this is the north star's looser-tolerance mode: Vs within 5e-3, log acceptance
+ratio within 0.1 (it is a sum of 513 terms)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from _util import load_golden
+from test_gpu_parity import _mcem_from_golden, _oracle_trace
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("N,K", [(128, 16), (128, 32), (128, 128), (16, 128), (176, 128), (256, 64)])
+def test_umma_selftest(N, K):
+    from gvn import _lib
+    lib = _lib.load()
+    torch.manual_seed(N * 1000 + K)
+    A = torch.randn(128, K, device="cuda")
+    W = torch.randn(N, K, device="cuda") * 0.1
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    ref16 = A.half().float() @ W.half().float().T
+    ref64 = (A.double() @ W.double().T)
+    for variant, ref, tol in ((0, ref16, 2e-5), (4, ref64.float(), 5e-5)):
+        D = torch.full((128, N), float("nan"), device="cuda")
+        _lib.check(lib.gvn_selftest_umma(C.c_void_p(A.data_ptr()), C.c_void_p(W.data_ptr()), N, K, variant,
+                                         C.c_void_p(D.data_ptr()), st))
+        torch.cuda.synchronize()
+        assert float((D - ref).abs().max()) < tol * max(1.0, float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("tag", ["M2_ibm", "M1", "M2_vad"])
+def test_tc_chain_matches_fp32_chain(tag):
+    """Same state, same noise, same (forced) decisions: f16 tensor-core chain vs fp32 chain."""
+    g = load_golden(tag)
+    o, cost_o, acc_o, dec_o, logu_o, snaps = _oracle_trace(g)
+    out = {}
+    for prec in ("fp32", "f16"):
+        m = _mcem_from_golden(g, forced=dec_o, precision=prec)
+        (R, burnin), _ = m.chain_lengths()
+        m._run_chain(R, burnin, trace=True)
+        torch.cuda.synchronize()
+        out[prec] = dict(acc=m.last_trace["acc_prob"].cpu().numpy(), Vs=m.Vs.cpu().numpy(), Z=m.Z.cpu().numpy(),
+                         zs=m.last_trace["z_samples"].cpu().numpy(), cnt=m.last_trace["n_accepted"].cpu().numpy())
+    a, b = out["fp32"], out["f16"]
+    np.testing.assert_array_equal(a["cnt"], b["cnt"])
+    np.testing.assert_allclose(b["Z"], a["Z"], rtol=1e-6, atol=1e-6)            # forced decisions: same path
+    np.testing.assert_allclose(b["zs"], a["zs"], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(b["Vs"], a["Vs"], rtol=5e-3)
+    np.testing.assert_allclose(b["acc"], a["acc"], atol=0.1, rtol=2e-2)
+    # and against the oracle itself
+    n1 = R + burnin
+    np.testing.assert_allclose(b["acc"], acc_o[:n1], atol=0.1, rtol=2e-2)
+    np.testing.assert_allclose(b["Vs"], snaps[0]["Vs"], rtol=5e-3)
+
+
+@pytest.mark.parametrize("tag", ["M2_ibm", "M1"])
+def test_tc_full_run_forced(tag):
+    g = load_golden(tag)
+    o, cost_o, acc_o, dec_o, logu_o, snaps = _oracle_trace(g)
+    m = _mcem_from_golden(g, forced=dec_o, precision="f16")
+    cost = m.run()
+    np.testing.assert_allclose(cost, g["cost"], rtol=2e-3)
+    np.testing.assert_allclose(m.W.cpu().numpy(), g["M%d_W" % (int(g["niter"]) - 1)], rtol=2e-2, atol=1e-6)
+    np.testing.assert_allclose(m.S_hat, g["S_hat"], rtol=2e-2, atol=2e-3 * np.max(np.abs(g["S_hat"])))
+
+
+def test_tc_philox_matches_fp32_statistics():
+    """Free-running Philox chains at the benchmark shape: the f16 chain and the fp32 chain use the
+    same random stream, so costs agree closely and the final Wiener masks are statistically equal."""
+    from gvn import engine as E
+    from gvn.pipeline import McemConfig, Enhancer
+    from gvn.synth import synth_batch
+    from python.models.models import DeepGenerativeModel
+    from python.processing.target import clean_speech_IBM
+    from oracle import stft_oracle
+    kw = dict(fs=16000, wlen_sec=64e-3, win="hann", hop_percent=0.25)
+    torch.manual_seed(0)
+    vae = DeepGenerativeModel([513, 513, 16, [128, 128]], None).eval()
+    x, s, n = synth_batch(3, seed=0, T=64000)
+    labels = [clean_speech_IBM(stft_oracle.stft(si, dtype="complex64", **kw), 0.999, 0.999) for si in s]
+    res = {}
+    for prec in ("fp32", "f16"):
+        cfg = McemConfig(model="M2", niter=5, nmf_rank=10, precision=prec)
+        enh = Enhancer(vae, cfg, "cuda:0")
+        b = enh.prepare(list(x), labels, seed=5)
+        cost, S, Nn, WFs, WFn = E.run_mcem(b, enh.dec, cfg.niter, *cfg.chains(), cfg.var_RW, prec, seed=5, want_masks=True)
+        torch.cuda.synchronize()
+        res[prec] = (cost.cpu().numpy(), WFs.cpu().numpy())
+    assert np.all(np.isfinite(res["f16"][0]))
+    np.testing.assert_allclose(res["f16"][0], res["fp32"][0], rtol=1e-2)
+    assert np.mean(np.abs(res["f16"][1] - res["fp32"][1])) < 0.02
