@@ -166,7 +166,7 @@ def main():
     ap.add_argument("--niter", type=int, default=100)
     ap.add_argument("--rank-k", type=int, default=10)
     ap.add_argument("--precision", default=os.environ.get("GVN_PRECISION", "fp32"))
-    ap.add_argument("--mstep-variant", type=int, default=int(os.environ.get("GVN_MSTEP_VARIANT", "0")))
+    ap.add_argument("--mstep-variant", type=int, default=int(os.environ.get("GVN_MSTEP_VARIANT", "1")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -113,7 +113,8 @@ __global__ void __launch_bounds__(256) k_mstep_cols(int F, int K, int NP, int R,
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile = blockIdx.x, gn = tile * MS_TILE + lane;
   const int b = frame_utt[tile * MS_TILE];
-  if (b < 0) { if (threadIdx.x == 0) cost_part[tile] = 0.f; return; }
+  if (threadIdx.x < 4) cost_part[tile * 4 + threadIdx.x] = 0.f;     // cost_part is indexed by GVN_COST_TILE (8) frames
+  if (b < 0) return;
   const bool valid = frame_utt[gn] >= 0;
   const float* wb = Wun + (size_t)b * F * K;
   const size_t slab = (size_t)F * NP;
@@ -218,7 +219,7 @@ __global__ void __launch_bounds__(256) k_mstep_cols(int F, int K, int NP, int R,
   if (threadIdx.x == 0) {
     float s = 0.f;
     for (int w = 0; w < MS_WARPS; ++w) s += red1[w];
-    cost_part[tile] = s;
+    cost_part[tile * 4] = s;
   }
   // normalised H (mcem.py:133) and new g
   if (warp == 0 && valid) {
@@ -234,7 +235,7 @@ __global__ void k_cost_reduce(int B, int F, int R, int niter, int ntiles, const 
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= niter * B) return;
   int it = i / B, b = i % B;
-  int t0 = frame_off[b] / MS_TILE, t1 = (frame_off[b] + n_frames[b] + MS_TILE - 1) / MS_TILE;
+  int t0 = frame_off[b] / GVN_COST_TILE, t1 = (frame_off[b] + n_frames[b] + MS_TILE - 1) / MS_TILE * (MS_TILE / GVN_COST_TILE);
   double s = 0.0;
   for (int t = t0; t < t1; ++t) s += (double)part[(size_t)it * ntiles + t];
   cost[i] = s / ((double)R * F * n_frames[b]);
@@ -305,8 +306,12 @@ __global__ void k_init_nmf_cols(int F, int K, int NP, const int32_t* __restrict_
 
 size_t mstep_workspace_bytes(const gvn_batch* b) { return (size_t)b->B * b->K * sizeof(float); }
 
+bool mstep_v1_supported(const gvn_batch*, int);
+int32_t launch_mstep_v1(const gvn_batch*, int, float*, cudaStream_t);
+
 int32_t launch_mstep(const gvn_batch* b, int R, float* cost_part, void* workspace, int variant, cudaStream_t st) {
-  (void)variant;
+  // variant 0: reference schedule (any shape); variant 1 (default when the tile fits in shared memory): mstep_v1.cu
+  if (variant != 0 && mstep_v1_supported(b, R)) return launch_mstep_v1(b, R, cost_part, st);
   float* cnorm = reinterpret_cast<float*>(workspace);
   dim3 gw((b->F + MS_WARPS - 1) / MS_WARPS, b->B);
   const int ntiles = b->NP / MS_TILE;
@@ -333,7 +338,7 @@ int32_t launch_mstep(const gvn_batch* b, int R, float* cost_part, void* workspac
 
 int32_t launch_cost_reduce(const gvn_batch* b, int R, int niter, const float* part, double* cost, cudaStream_t st) {
   int n = niter * b->B;
-  k_cost_reduce<<<(n + 127) / 128, 128, 0, st>>>(b->B, b->F, R, niter, b->NP / MS_TILE, b->frame_off, b->n_frames,
+  k_cost_reduce<<<(n + 127) / 128, 128, 0, st>>>(b->B, b->F, R, niter, b->NP / GVN_COST_TILE, b->frame_off, b->n_frames,
                                                  part, cost);
   return check_launch("k_cost_reduce");
 }

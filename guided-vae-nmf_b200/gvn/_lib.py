@@ -8,6 +8,7 @@ LIB_PATH = os.path.join(os.path.dirname(_HERE), "libgvn.so")
 
 GVN_FRAME_ALIGN = 32
 GVN_HIDDEN = 128
+GVN_COST_TILE = 8
 GVN_MAX_K = 32
 GVN_MAX_L = 64
 PREC_FP32, PREC_F16X3, PREC_F16 = 0, 1, 2

@@ -314,11 +314,11 @@ class MstepScratch:
     def __init__(self, batch, niter):
         lib = _lib.load()
         self.ws = torch.empty(max(16, lib.gvn_mstep_workspace_bytes(batch.struct())), dtype=torch.uint8, device=batch.device)
-        self.ntiles = batch.NP // GVN_FRAME_ALIGN
+        self.ntiles = batch.NP // _lib.GVN_COST_TILE
         self.cost_part = torch.zeros(niter, self.ntiles, dtype=torch.float32, device=batch.device)
 
 
-def mstep(batch, R, scratch, it, variant=0):
+def mstep(batch, R, scratch, it, variant=1):
     lib = _lib.load()
     check(lib.gvn_mstep(batch.struct(), int(R), _ptr(scratch.cost_part[it]), _ptr(scratch.ws), int(variant), _stream()))
 
@@ -362,7 +362,7 @@ class KernelTimers:
 
 
 def run_mcem(batch, dec, niter, chain_E, chain_WF, var_RW, precision="fp32", seed=0, noise=None,
-             mstep_variant=0, want_masks=False, iter_hook=None, timers=None):
+             mstep_variant=1, want_masks=False, iter_hook=None, timers=None):
     """EM.run (mcem.py:155-178) for the whole batch: niter x (E-step chain, M-step), then the
     Wiener chain.  chain_E / chain_WF are (R, burnin).  Returns (cost[niter][B] f64 device
     tensor, S_hat, N_hat, WFs, WFn).  Nothing here synchronises the host."""

@@ -31,7 +31,7 @@ class McemConfig:
     wlen_sec: float = 64e-3
     hop_percent: float = 0.25
     precision: str = "fp32"
-    mstep_variant: int = 0
+    mstep_variant: int = 1
 
     def chains(self):
         """(R, burnin) of the E-step and Wiener chains, incl. the M1 quirk (mcem.py:461-462)."""

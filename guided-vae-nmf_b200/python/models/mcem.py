@@ -32,7 +32,7 @@ class EM:
         self.niter = niter
         self.Vs = None
         self.precision = "fp32"        # "fp32" | "f16x3" | "f16"  (decoder arithmetic)
-        self.mstep_variant = 0
+        self.mstep_variant = 1
         self.seed = None               # Philox seed; None -> derived from torch's seed
         self.replay = None             # dict(rand_W, rand_H, eps, u[, forced]) for parity runs
         self._batch = None

@@ -46,6 +46,7 @@ extern "C" {
 
 #define GVN_VERSION 100
 #define GVN_FRAME_ALIGN 32      /* utterances start on multiples of this many frames   */
+#define GVN_COST_TILE 8        /* frames per partial cost sum written by gvn_mstep       */
 #define GVN_HIDDEN 128          /* decoder hidden width (h_dim=[128,128] in every script) */
 #define GVN_MAX_K 32            /* NMF rank limit */
 #define GVN_MAX_L 64            /* latent dimension limit */
@@ -127,12 +128,14 @@ int32_t gvn_estep(const gvn_batch* batch /*HOST*/, const void* packed, int32_t b
 
 /* NMF / gain M-step: replaces EM.M_step + compute_expected_neg_log_like
  * (mcem.py:90-152, :68-70).  Updates W, H, g, Vb in place; cost_part receives one partial
- * sum per 32-frame tile ([NP/32]); gvn_cost_reduce turns niter of them into cost[niter][B]. */
+ * sum per GVN_COST_TILE frames ([NP/8]); gvn_cost_reduce turns niter of them into cost[niter][B].
+ * variant 0: straightforward schedule, any shape.  variant 1: HBM-bound schedule (column tiles
+ * staged once in shared memory); falls back to 0 when the tile does not fit (K > 12 at R = 10). */
 size_t gvn_mstep_workspace_bytes(const gvn_batch* batch /*HOST*/);
 int32_t gvn_mstep(const gvn_batch* batch /*HOST*/, int32_t R, float* cost_part, void* workspace,
                   int32_t variant, void* stream);
 int32_t gvn_cost_reduce(const gvn_batch* batch /*HOST*/, int32_t R, int32_t niter,
-                        const float* cost_part /*[niter][NP/32]*/, double* cost /*[niter][B]*/,
+                        const float* cost_part /*[niter][NP/8]*/, double* cost /*[niter][B]*/,
                         void* stream);
 
 /* Wiener filter from the R kept samples of the final chain: replaces the tail of
