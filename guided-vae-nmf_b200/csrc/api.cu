@@ -49,7 +49,7 @@ static int32_t check_batch(const gvn_batch* b, bool need_state) {
   GVN_REQUIRE(b->frame_off && b->n_frames && b->frame_utt, GVN_E_INVALID, "frame index arrays are NULL");
   if (need_state) {
     GVN_REQUIRE(b->K >= 1 && b->K <= GVN_MAX_K, GVN_E_UNSUPPORTED_SHAPE, "NMF rank K=%d outside [1,%d]", b->K, GVN_MAX_K);
-    GVN_REQUIRE(b->X2 && b->W && b->Wun && b->H && b->g && b->Vb && b->Vs, GVN_E_INVALID, "batch state pointer is NULL");
+    GVN_REQUIRE(b->X2 && b->W && b->Wun && b->H && b->g && b->Vb && b->Vs && b->Vs_w, GVN_E_INVALID, "batch state pointer is NULL");
   }
   return GVN_OK;
 }

@@ -5,7 +5,7 @@
 // :371-454).  Differences in *how*, not *what*:
 //   * the decoder is evaluated once per proposal; the reference's second sweep after the
 //     accept (mcem.py:283) and its re-decode of the kept samples (mcem.py:300) are replaced
-//     by select / copy of the values already computed;
+//     by the values already computed, kept in slot form (Vs + multiplicities Vs_w, gvn.h);
 //   * the current-state part of the log acceptance ratio (mcem.py:266-268) is cached per
 //     frame as C_t = sum_f log Vx_t + X2/Vx_t and only refreshed on accept;
 //   * the label columns of the first layer are hoisted into `yproj` (gvn_label_projection).
@@ -26,7 +26,7 @@ struct EstepArgs {
   float sd;                    // sqrt(var_RW) in fp32, as mcem.py:231,257
   const int32_t* frame_utt;
   const float* X2; const float* g; const float* Vb; const float* yproj;
-  float* Z; float* Vs;
+  float* Z; float* Vs; float* Vs_w;
   // decoder (fp32 section of the packed image)
   const float* w1zT; const float* w2T; const float* b2; const float* w3T; const float* b3; int FS;
   // noise
@@ -102,6 +102,8 @@ __global__ void __launch_bounds__(NT, 2) k_estep_simt(EstepArgs p) {
   int* sAcc = reinterpret_cast<int*>(sG + TN);          // [TN] decision of this step
   int* sCnt = sAcc + TN;                                // [TN] accepted count
   int* sValid = sCnt + TN;                              // [TN]
+  int* sCur = sValid + TN;                              // [TN] slot holding the current state
+  float* sMul = reinterpret_cast<float*>(sCur + TN);    // [TN] its multiplicity so far
 
   const int tid = threadIdx.x, tg = tid & 15, fg = tid >> 4;
   const int warp = tid >> 5, lane = tid & 31;
@@ -114,6 +116,9 @@ __global__ void __launch_bounds__(NT, 2) k_estep_simt(EstepArgs p) {
     sG[tid] = v ? p.g[n] : 1.f;
     sCnt[tid] = 0;
     sAcc[tid] = 0;
+    sCur[tid] = 0;
+    sMul[tid] = 0.f;
+    if (v) for (int s = 0; s < p.R; ++s) p.Vs_w[(size_t)s * NP + n] = 0.f;
   }
   for (int idx = tid; idx < L * TN; idx += NT) {
     int l = idx / TN, c = idx % TN, n = n0 + c;
@@ -259,6 +264,12 @@ __global__ void __launch_bounds__(NT, 2) k_estep_simt(EstepArgs p) {
       }
       sAcc[tid] = ok;
       if (ok) { sCt[tid] = sCp[tid]; sCnt[tid] += 1; }
+      // multiplicities of the kept samples: a rejected step repeats the state (mcem.py:280-289)
+      if (r == 0) { sCur[tid] = 0; sMul[tid] = 1.f; }
+      else if (r >= 1) {
+        if (ok) { if (sValid[tid]) p.Vs_w[(size_t)sCur[tid] * NP + n] = sMul[tid]; sCur[tid] = r; sMul[tid] = 1.f; }
+        else sMul[tid] += 1.f;
+      }
     }
     __syncthreads();
     for (int idx = tid; idx < L * TN; idx += NT)
@@ -272,17 +283,9 @@ __global__ void __launch_bounds__(NT, 2) k_estep_simt(EstepArgs p) {
         if (n < NP && sValid[c]) p.t_zs[((size_t)r * L + l) * NP + n] = sZ[idx];
       }
     }
-    if (r == 0) {
-      decode(sZ, MODE_WRITE, p.Vs);
-    } else if (r >= 1) {
-      const float* prev = p.Vs + (size_t)(r - 1) * F * NP;
-      for (int idx = tid; idx < F * TN; idx += NT) {
-        int f = idx / TN, c = idx % TN;
-        if (!sAcc[c] && n0 + c < NP) spec[(size_t)f * NP + n0 + c] = prev[(size_t)f * NP + n0 + c];
-      }
-      __syncthreads();
-    }
+    if (r == 0) decode(sZ, MODE_WRITE, p.Vs);
   }
+  if (tid < TN && sValid[tid]) p.Vs_w[(size_t)sCur[tid] * NP + n0 + tid] = sMul[tid];
 
   for (int idx = tid; idx < L * TN; idx += NT) {
     int l = idx / TN, c = idx % TN, n = n0 + c;
@@ -293,7 +296,7 @@ __global__ void __launch_bounds__(NT, 2) k_estep_simt(EstepArgs p) {
 
 size_t estep_simt_smem(int L) {
   return (size_t)(2 * L * TN + 2 * HID * TN + 2 * KT * HID) * 4 + (size_t)(8 * TN + 2 * TN) * 8 +
-         (size_t)TN * 4 * 4;
+         (size_t)TN * 4 * 6;
 }
 
 }  // namespace
@@ -306,7 +309,7 @@ int32_t launch_estep_simt(const gvn_batch* b, const void* packed, int burnin, in
   a.F = b->F; a.L = b->L; a.NP = b->NP; a.burnin = burnin; a.R = R;
   a.sd = sqrtf(var_RW);
   a.frame_utt = b->frame_utt; a.X2 = b->X2; a.g = b->g; a.Vb = b->Vb; a.yproj = b->yproj;
-  a.Z = b->Z; a.Vs = b->Vs;
+  a.Z = b->Z; a.Vs = b->Vs; a.Vs_w = b->Vs_w;
   a.w1zT = base + d.w1zT; a.w2T = base + d.w2T; a.b2 = base + d.b2; a.w3T = base + d.w3T;
   a.b3 = base + d.b3; a.FS = d.FS;
   a.eps = nz->eps; a.u = nz->u; a.forced = nz->forced_accept; a.seed = nz->seed; a.chain = nz->chain;

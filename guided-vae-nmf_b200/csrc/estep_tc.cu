@@ -31,6 +31,16 @@ __global__ void k_pack_plane(const float* __restrict__ W, int ldw, int col0, int
   }
 }
 
+// [128][2*L16] image of [W1z | W1z] (hi plane only): the A operand carries z as an f16 hi | lo pair
+__global__ void k_pack_w1dup(const float* __restrict__ W1, int ldw, int L, int L16, float scale, unsigned char* __restrict__ img) {
+  const int K = 2 * L16;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < GVN_HIDDEN * K; i += gridDim.x * blockDim.x) {
+    const int n = i / K, k = i % K, l = k % L16;
+    const float w = (l < L) ? W1[(size_t)n * ldw + l] * scale : 0.f;
+    *reinterpret_cast<__half*>(img + img_offset(n, k, K)) = __float2half_rn(w);
+  }
+}
+
 __global__ void k_pack_bias(const float* __restrict__ b3, int F, int FN, float* __restrict__ b3s) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < FN) b3s[i] = i < F ? b3[i] * 1.4426950408889634f : 0.f;
@@ -124,6 +134,7 @@ int32_t launch_pack_tc(const float* W1, const float* W2, const float* W3, const 
   k_pack_plane<<<32, 256, 0, st>>>(W1, L + y_dim, 0, H, L, H, t.L16, W_SCALE, image + t.w1, image + t.w1 + t.plane_w1);
   k_pack_plane<<<64, 256, 0, st>>>(W2, H, 0, H, H, H, H, W_SCALE, image + t.w2, image + t.w2 + t.plane_w2);
   k_pack_plane<<<148, 256, 0, st>>>(W3, H, 0, F, H, t.FN, H, W_SCALE, image + t.w3, image + t.w3 + t.plane_w3);
+  k_pack_w1dup<<<32, 256, 0, st>>>(W1, L + y_dim, L, t.L16, W_SCALE, image + t.w1d);
   k_pack_bias<<<(t.FN + 255) / 256, 256, 0, st>>>(b3, F, t.FN, reinterpret_cast<float*>(image + t.b3s));
   return check_launch("k_pack_tc");
 }

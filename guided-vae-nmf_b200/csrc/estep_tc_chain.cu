@@ -8,16 +8,28 @@
 //     the log acceptance ratio (mcem.py:266-268) is a private register accumulation;
 //   * activations never touch shared memory: the epilogue threads write tanh(.) as packed f16
 //     straight into TMEM (tcgen05.st) and the next layer's MMA reads its A operand from there;
+//     the latent z goes in as an f16 hi+lo pair against a duplicated W1 (K = 2*L), so the
+//     random walk itself keeps fp32 resolution;
 //   * weights sit in shared memory for the whole chain as UMMA operand images (packed once by
 //     gvn_pack_decoder; f16 because activations are in [-1,1] and weights O(0.05): 11 mantissa
 //     bits = TF32 precision at twice the MMA rate and half the footprint);
 //   * the output layer (F=513 -> 4 chunks of 128 columns + one of 16) is double-buffered in TMEM:
 //     the MMA of chunk c+1 runs while the epilogue consumes chunk c;
-//   * X2 and Vb stream through a TMA ring ([16 frequency rows][128 frames] boxes of the
-//     frame-minor arrays), produced by a dedicated warp.
+//   * the per-bin constants of the chain, X2 and Vb, are packed once per launch into one 32-bit
+//     word per (f, frame) (bf16 pair; both appear on the two sides of the acceptance ratio, so the
+//     rounding is a fixed perturbation of the target density, not noise) and stream through a TMA
+//     ring of [32 frequency rows][128 frames] boxes, produced by a dedicated warp;
+//   * the epilogue is MUFU-bound (exp per bin, log and reciprocal of Vx): bins are processed in
+//     pairs, log a + log b = log(ab) and x/a + y/b = (xb + ya)/(ab), one lg2 and one rcp per pair.
+// Kept samples: slot r of Vs receives the proposal of kept step r (speculative store from the
+// epilogue); Vs_w[r][n] is the multiplicity of slot r (0 when that proposal was rejected, k+1 when
+// the k following proposals were) -- see include/gvn.h.
 // Warp roles: 0-7 epilogue (warp w and w+4 share TMEM lane quarter w%4 and split the columns),
 // 8 = MMA issuer (one elected lane), 9 = TMA producer (one elected lane).
 #include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <type_traits>
 
 #include "gvn_common.cuh"
 #include "tc_common.cuh"
@@ -31,24 +43,27 @@ namespace {
 constexpr int TM = 128;                 // frames per tile (MMA M)
 constexpr int HID = GVN_HIDDEN;
 constexpr int NE = 256;                 // epilogue threads
+constexpr int NEW = NE / 32;            // epilogue warps
 constexpr int NTHREADS = 320;
-constexpr int SUB = 16;                 // frequency rows per TMA box
-constexpr int STAGE_BYTES = 2 * SUB * TM * 4;
+constexpr int SROWS = 32;               // frequency rows per TMA box
+constexpr int STAGE_BYTES = SROWS * TM * 4;
+constexpr int MAX_STAGES = 8;
 constexpr float W_SCALE_INV = 1.0f / 256.0f;
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
+constexpr float SC3 = W_SCALE_INV * LOG2E;
 
 // TMEM column map (512 columns allocated)
-constexpr uint32_t COL_ACC0 = 0, COL_ACC1 = 128, COL_A_HI = 256, COL_A_LO = 320, COL_Z_HI = 384, COL_Z_LO = 416;
+constexpr uint32_t COL_ACC0 = 0, COL_ACC1 = 128, COL_ACCH = 256, COL_A = 384, COL_Z = 448;
 
 struct TcArgs {
   int F, FN, L, NP, burnin, R, nstage;
   float sd;
   const int32_t* frame_utt;
   const float* g; const float* yproj;
-  float* Z; float* Vs;
+  float* Z; float* Vs; float* Vs_w;
   const unsigned char* img;            // tensor-core operand image
-  size_t off_w1, off_w2, off_w3, off_b3s;
+  size_t off_w1d, off_w2, off_w3, off_b3s;
   const float* b2;
   const float* eps; const float* u; const uint8_t* forced; uint64_t seed, chain;
   float* t_acc; uint8_t* t_dec; int32_t* t_cnt; float* t_zs;
@@ -61,31 +76,44 @@ __device__ __forceinline__ float tanh_approx(float x) { float y; asm("tanh.appro
 
 __device__ __forceinline__ void bar_epilogue() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-enum { MODE_INIT = 0, MODE_PROP = 1, MODE_WRITE = 2 };
+// XV[f][n] = bf16(X2) << 16 | bf16(Vb)
+__global__ void __launch_bounds__(256) k_pack_xv(size_t n4, const float4* __restrict__ X2, const float4* __restrict__ Vb,
+                                                 uint4* __restrict__ XV) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 x = X2[i], v = Vb[i];
+    uint4 o;
+    __nv_bfloat162 t;
+    t = __floats2bfloat162_rn(v.x, x.x); o.x = *reinterpret_cast<uint32_t*>(&t);
+    t = __floats2bfloat162_rn(v.y, x.y); o.y = *reinterpret_cast<uint32_t*>(&t);
+    t = __floats2bfloat162_rn(v.z, x.z); o.z = *reinterpret_cast<uint32_t*>(&t);
+    t = __floats2bfloat162_rn(v.w, x.w); o.w = *reinterpret_cast<uint32_t*>(&t);
+    XV[i] = o;
+  }
+}
 
 template <int L16>
-__global__ void __launch_bounds__(NTHREADS, 1) k_estep_tc(const __grid_constant__ CUtensorMap tm_x2,
-                                                          const __grid_constant__ CUtensorMap tm_vb, TcArgs p) {
+__global__ void __launch_bounds__(NTHREADS, 1) k_estep_tc(const __grid_constant__ CUtensorMap tm_xv, TcArgs p) {
+  constexpr int K1 = 2 * L16;                             // z hi | z lo against [W1 | W1]
   extern __shared__ __align__(1024) unsigned char smem[];
   const int F = p.F, FN = p.FN, NP = p.NP, L = p.L;
   const int NCH = (FN + 127) / 128;                       // output-layer chunks (last one may be 16 wide)
   // ---- shared memory carve-up ----
-  unsigned char* sW1 = smem;                              // [128][L16] f16 image
-  unsigned char* sW2 = sW1 + HID * L16 * 2;               // [128][128]
+  unsigned char* sW1 = smem;                              // [128][K1] f16 image
+  unsigned char* sW2 = sW1 + HID * K1 * 2;                // [128][128]
   unsigned char* sW3 = sW2 + HID * HID * 2;               // [FN][128]
-  unsigned char* sRing = sW3 + (size_t)FN * HID * 2;      // nstage x {X2 [16][128] f32, Vb [16][128] f32}
-  float* sB3 = reinterpret_cast<float*>(sRing + (size_t)p.nstage * STAGE_BYTES);   // [FN]  b3*log2e
-  float* sB2 = sB3 + FN;                                  // [128]
-  double* sPart = reinterpret_cast<double*>(sB2 + HID);   // [256]
-  int* sAcc = reinterpret_cast<int*>(sPart + NE);         // [128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sAcc + TM);
+  unsigned char* sRing = sW3 + (size_t)FN * HID * 2;      // nstage x [32][128] u32 (bf16 X2 | bf16 Vb)
+  float* sB3 = reinterpret_cast<float*>(sRing + (size_t)p.nstage * STAGE_BYTES);   // [FN + 16]  b3*log2e
+  float* sB2 = sB3 + FN + 16;                             // [128]
+  double* sPart = reinterpret_cast<double*>(sB2 + HID);   // [2][256]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sPart + 2 * NE);
   uint64_t* bar_z = bars + 0;                             // E(0-3) -> M : Z operand in TMEM
-  uint64_t* bar_h = bars + 1;                             // E -> M : hidden activations in TMEM
-  uint64_t* bar_d = bars + 2;                             // [2] M -> E : accumulator buffer full
-  uint64_t* bar_free = bars + 4;                          // [2] E -> M : accumulator buffer drained
-  uint64_t* bar_full = bars + 6;                          // [nstage] TMA -> E
-  uint64_t* bar_empty = bars + 6 + 8;                     // [nstage] E -> P
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6 + 16);
+  uint64_t* bar_h = bars + 1;                             // E -> M : hidden activations in TMEM, ACCH drained
+  uint64_t* bar_hfull = bars + 2;                         // M -> E : hidden-layer accumulator full
+  uint64_t* bar_d = bars + 3;                             // [2] M -> E : accumulator buffer full
+  uint64_t* bar_free = bars + 5;                          // [2] E -> M : accumulator buffer drained
+  uint64_t* bar_full = bars + 7;                          // [nstage] TMA -> E
+  uint64_t* bar_empty = bars + 7 + MAX_STAGES;            // [nstage] E -> P
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7 + 2 * MAX_STAGES);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n0 = blockIdx.x * TM;
@@ -93,21 +121,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_estep_tc(const __grid_constant_
   // ---- one-time setup: weights -> smem, barriers, TMEM ----
   {
     const uint4* src; uint4* dst; int n16;
-    src = reinterpret_cast<const uint4*>(p.img + p.off_w1); dst = reinterpret_cast<uint4*>(sW1); n16 = HID * L16 * 2 / 16;
+    src = reinterpret_cast<const uint4*>(p.img + p.off_w1d); dst = reinterpret_cast<uint4*>(sW1); n16 = HID * K1 * 2 / 16;
     for (int i = tid; i < n16; i += NTHREADS) dst[i] = src[i];
     src = reinterpret_cast<const uint4*>(p.img + p.off_w2); dst = reinterpret_cast<uint4*>(sW2); n16 = HID * HID * 2 / 16;
     for (int i = tid; i < n16; i += NTHREADS) dst[i] = src[i];
     src = reinterpret_cast<const uint4*>(p.img + p.off_w3); dst = reinterpret_cast<uint4*>(sW3); n16 = FN * HID * 2 / 16;
     for (int i = tid; i < n16; i += NTHREADS) dst[i] = src[i];
     const float* b3s = reinterpret_cast<const float*>(p.img + p.off_b3s);
-    for (int i = tid; i < FN; i += NTHREADS) sB3[i] = b3s[i];
+    for (int i = tid; i < FN + 16; i += NTHREADS) sB3[i] = i < FN ? b3s[i] : 0.f;
     for (int i = tid; i < HID; i += NTHREADS) sB2[i] = p.b2[i];
   }
   if (tid == 0) {
-    mbar_init(bar_z, 128);
-    mbar_init(bar_h, NE);
-    for (int i = 0; i < 2; ++i) { mbar_init(bar_d + i, 1); mbar_init(bar_free + i, NE); }
-    for (int i = 0; i < p.nstage; ++i) { mbar_init(bar_full + i, 1); mbar_init(bar_empty + i, NE); }
+    mbar_init(bar_z, 4);
+    mbar_init(bar_h, NEW);
+    mbar_init(bar_hfull, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(bar_d + i, 1); mbar_init(bar_free + i, NEW); }
+    for (int i = 0; i < p.nstage; ++i) { mbar_init(bar_full + i, 1); mbar_init(bar_empty + i, NEW); }
     mbar_init_fence();
   }
   if (warp == 8) tmem_alloc(tmem_slot, 512);
@@ -118,8 +147,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_estep_tc(const __grid_constant_
   const uint32_t tbase = *tmem_slot;
 
   const int n_steps = p.burnin + p.R;
-  // number of decoder passes with X2/Vb streaming and the pass schedule are the same for all roles:
-  //   INIT, then per step m: PROP, and WRITE after the step with m == burnin.
+  const int NST = (F + SROWS - 1) / SROWS;                // ring stages per streaming pass
+  // pass schedule, identical for all roles: INIT, then per step m: PROP, and WRITE after the step m == burnin
 
   if (warp == 9) {
     // =============================== TMA producer ===============================
@@ -127,13 +156,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_estep_tc(const __grid_constant_
       uint32_t it = 0;
       const int n_load_passes = 1 + n_steps;
       for (int ps = 0; ps < n_load_passes; ++ps) {
-        for (int f0 = 0; f0 < FN; f0 += SUB, ++it) {
+        for (int s = 0; s < NST; ++s, ++it) {
           const uint32_t slot = it % p.nstage, par = ((it / p.nstage) & 1) ^ 1;
           mbar_wait(bar_empty + slot, par);
           mbar_expect_tx(bar_full + slot, STAGE_BYTES);
-          unsigned char* dst = sRing + (size_t)slot * STAGE_BYTES;
-          tma_load_2d(dst, &tm_x2, n0, f0, bar_full + slot);
-          tma_load_2d(dst + SUB * TM * 4, &tm_vb, n0, f0, bar_full + slot);
+          tma_load_2d(sRing + (size_t)slot * STAGE_BYTES, &tm_xv, n0, s * SROWS, bar_full + slot);
         }
       }
     }
@@ -141,25 +168,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_estep_tc(const __grid_constant_
     // =============================== MMA issuer ===============================
     if (lane == 0) {
       uint32_t n_z = 0, n_h = 0, n_free[2] = {0, 0};
-      const uint32_t sbo1 = img_sbo(L16), sbo = img_sbo(HID), lbo = img_lbo();
+      const uint32_t sbo1 = img_sbo(K1), sbo = img_sbo(HID), lbo = img_lbo();
       const int n_pass = 1 + n_steps + (p.R > 0 ? 1 : 0);
       for (int ps = 0; ps < n_pass; ++ps) {
-        // layer 1: ACC0[:, 0:128] = Z(128 x L16) * W1^T
-        mbar_wait(bar_free + 0, (n_free[0]++ & 1) ^ 1);
+        // layer 1: ACCH = [z_hi | z_lo](128 x K1) * [W1 | W1]^T
         mbar_wait(bar_z, n_z++ & 1);
         fence_after();
-        for (int k0 = 0; k0 < L16; k0 += 16)
-          mma_ts(tbase + COL_ACC0, tbase + COL_Z_HI + k0 / 2, smem_desc(smem_u32(sW1) + (k0 / 8) * 128, lbo, sbo1),
+#pragma unroll
+        for (int k0 = 0; k0 < K1; k0 += 16)
+          mma_ts(tbase + COL_ACCH, tbase + COL_Z + k0 / 2, smem_desc(smem_u32(sW1) + (k0 / 8) * 128, lbo, sbo1),
                  idesc_f16(TM, HID), k0 > 0);
-        mma_commit(bar_d + 0);
-        // layer 2: ACC1[:, 0:128] = H1(128 x 128) * W2^T
-        mbar_wait(bar_free + 1, (n_free[1]++ & 1) ^ 1);
+        mma_commit(bar_hfull);
+        // layer 2: ACCH = H1(128 x 128) * W2^T
         mbar_wait(bar_h, n_h++ & 1);
         fence_after();
+#pragma unroll
         for (int k0 = 0; k0 < HID; k0 += 16)
-          mma_ts(tbase + COL_ACC1, tbase + COL_A_HI + k0 / 2, smem_desc(smem_u32(sW2) + (k0 / 8) * 128, lbo, sbo),
+          mma_ts(tbase + COL_ACCH, tbase + COL_A + k0 / 2, smem_desc(smem_u32(sW2) + (k0 / 8) * 128, lbo, sbo),
                  idesc_f16(TM, HID), k0 > 0);
-        mma_commit(bar_d + 1);
+        mma_commit(bar_hfull);
         // layer 3: chunks of the output features, alternating accumulator buffers
         mbar_wait(bar_h, n_h++ & 1);
         fence_after();
@@ -168,9 +195,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_estep_tc(const __grid_constant_
           mbar_wait(bar_free + buf, (n_free[buf]++ & 1) ^ 1);
           fence_after();
           const uint32_t b0 = smem_u32(sW3) + (uint32_t)(c * 16) * sbo;
+          const uint32_t idesc = idesc_f16(TM, ncol);
+#pragma unroll
           for (int k0 = 0; k0 < HID; k0 += 16)
-            mma_ts(tbase + (buf ? COL_ACC1 : COL_ACC0), tbase + COL_A_HI + k0 / 2, smem_desc(b0 + (k0 / 8) * 128, lbo, sbo),
-                   idesc_f16(TM, ncol), k0 > 0);
+            mma_ts(tbase + (buf ? COL_ACC1 : COL_ACC0), tbase + COL_A + k0 / 2, smem_desc(b0 + (k0 / 8) * 128, lbo, sbo),
+                   idesc, k0 > 0);
           mma_commit(bar_d + buf);
         }
       }
@@ -183,118 +212,170 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_estep_tc(const __grid_constant_
     const bool in_range = n < NP;
     const bool valid = in_range && p.frame_utt[n] >= 0;
     const float g = valid ? p.g[n] : 1.f;
-    uint32_t n_d[2] = {0, 0}, it = 0;
+    uint32_t n_d[2] = {0, 0}, n_hf = 0, it = 0, n_dec = 0;
     float z[L16], zp[L16];
+    uint32_t yp[32];                                      // label projection + b1 of this thread's 64 hidden units (f16 pairs)
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      yp[i] = in_range ? pack_f16(p.yproj[(size_t)(64 * half + 2 * i) * NP + n], p.yproj[(size_t)(64 * half + 2 * i + 1) * NP + n]) : 0u;
     double Ct = 0.0;
     int n_acc = 0;
     if (half == 0) {
 #pragma unroll
       for (int l = 0; l < L16; ++l) z[l] = (l < L && in_range) ? p.Z[(size_t)l * NP + n] : 0.f;
+      if (valid) for (int s = 0; s < p.R; ++s) p.Vs_w[(size_t)s * NP + n] = 0.f;
     }
 
-    auto put_z = [&](const float (&zz)[L16]) {       // warps 0-3: Z operand -> TMEM, signal the issuer
+    auto put_z = [&](const float (&zz)[L16]) {       // warps 0-3: Z operand (hi | lo) -> TMEM, signal the issuer
 #pragma unroll
       for (int k0 = 0; k0 < L16; k0 += 16) {
-        uint32_t hi[8];
+        uint32_t hi[8], lo[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) hi[j] = pack_f16(zz[k0 + 2 * j], zz[k0 + 2 * j + 1]);
-        tmem_st8(tlane + COL_Z_HI + k0 / 2, hi);
+        for (int j = 0; j < 8; ++j) {
+          const float a0 = zz[k0 + 2 * j], a1 = zz[k0 + 2 * j + 1];
+          const __half h0 = __float2half_rn(a0), h1 = __float2half_rn(a1);
+          hi[j] = pack_f16(__half2float(h0), __half2float(h1));
+          lo[j] = pack_f16(a0 - __half2float(h0), a1 - __half2float(h1));
+        }
+        tmem_st8(tlane + COL_Z + k0 / 2, hi);
+        tmem_st8(tlane + COL_Z + (L16 + k0) / 2, lo);
       }
       tmem_st_wait();
       fence_before();
-      mbar_arrive(bar_z);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_z);
     };
 
-    // one decoder evaluation; returns the energy sum_f log Vx + X2/Vx of this thread's row (half 0)
-    auto decode = [&](int mode, float* vs_out) -> double {
-      // ---- hidden layers: 64 columns per thread ----
-#pragma unroll 1
-      for (int layer = 0; layer < 2; ++layer) {
-        mbar_wait(bar_d + layer, n_d[layer]++ & 1);
-        fence_after();
-        const uint32_t acc_col = (layer ? COL_ACC1 : COL_ACC0) + 64 * half;
-#pragma unroll 1
-        for (int c0 = 0; c0 < 64; c0 += 16) {
-          uint32_t r[16];
-          tmem_ld16(tlane + acc_col + c0, r);
-          tmem_ld_wait();
-          uint32_t hi[8];
+    // hidden layer epilogue: tanh(acc/256 + bias) of this thread's 64 columns -> f16 A operand in TMEM
+    auto hidden = [&](auto layer0) {
+      mbar_wait(bar_hfull, n_hf++ & 1);
+      fence_after();
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int j0 = 64 * half + c0 + 2 * j;
-            float b0, b1;
-            if (layer == 0) {
-              b0 = in_range ? p.yproj[(size_t)j0 * NP + n] : 0.f;
-              b1 = in_range ? p.yproj[(size_t)(j0 + 1) * NP + n] : 0.f;
-            } else {
-              b0 = sB2[j0]; b1 = sB2[j0 + 1];
-            }
-            float h0 = tanh_approx(fmaf(__uint_as_float(r[2 * j]), W_SCALE_INV, b0));
-            float h1 = tanh_approx(fmaf(__uint_as_float(r[2 * j + 1]), W_SCALE_INV, b1));
-            hi[j] = pack_f16(h0, h1);
+      for (int c0 = 0; c0 < 64; c0 += 32) {
+        uint32_t r0[16], r1[16];
+        tmem_ld16(tlane + COL_ACCH + 64 * half + c0, r0);
+        tmem_ld16(tlane + COL_ACCH + 64 * half + c0 + 16, r1);
+        tmem_ld_wait();
+        uint32_t o0[8], o1[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float b00, b01, b10, b11;
+          if constexpr (decltype(layer0)::value) {
+            const float2 t0 = __half22float2(*reinterpret_cast<const __half2*>(&yp[c0 / 2 + j]));
+            const float2 t1 = __half22float2(*reinterpret_cast<const __half2*>(&yp[c0 / 2 + 8 + j]));
+            b00 = t0.x; b01 = t0.y; b10 = t1.x; b11 = t1.y;
+          } else {
+            const float2 t0 = *reinterpret_cast<const float2*>(sB2 + 64 * half + c0 + 2 * j);
+            const float2 t1 = *reinterpret_cast<const float2*>(sB2 + 64 * half + c0 + 16 + 2 * j);
+            b00 = t0.x; b01 = t0.y; b10 = t1.x; b11 = t1.y;
           }
-          tmem_st8(tlane + COL_A_HI + (64 * half + c0) / 2, hi);
+          o0[j] = pack_f16(tanh_approx(fmaf(__uint_as_float(r0[2 * j]), W_SCALE_INV, b00)),
+                           tanh_approx(fmaf(__uint_as_float(r0[2 * j + 1]), W_SCALE_INV, b01)));
+          o1[j] = pack_f16(tanh_approx(fmaf(__uint_as_float(r1[2 * j]), W_SCALE_INV, b10)),
+                           tanh_approx(fmaf(__uint_as_float(r1[2 * j + 1]), W_SCALE_INV, b11)));
         }
-        tmem_st_wait();
-        fence_before();
-        mbar_arrive(bar_free + layer);
-        mbar_arrive(bar_h);
+        tmem_st8(tlane + COL_A + (64 * half + c0) / 2, o0);
+        tmem_st8(tlane + COL_A + (64 * half + c0 + 16) / 2, o1);
       }
-      // ---- output layer: chunks, fused epilogue ----
+      tmem_st_wait();
+      fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_h);
+    };
+
+    // one decoder evaluation.  ENERGY: stream X2/Vb and return sum_f log Vx + X2/Vx of the row
+    // (valid in half 0); STORE: write the speech variance of the row to vs_out[f*NP] (f = 0..F)
+    auto decode = [&](auto energy_t, auto store_t, float* vs_out) -> double {
+      constexpr bool ENERGY = decltype(energy_t)::value, STORE = decltype(store_t)::value;
+      hidden(std::true_type{});
+      hidden(std::false_type{});
       double dl = 0.0, dr = 0.0;
+      float* vo = STORE ? vs_out + (size_t)(16 * half) * NP + n : nullptr;
 #pragma unroll 1
       for (int c = 0; c < NCH; ++c) {
         const int buf = c & 1, ncol = min(128, FN - c * 128);
         mbar_wait(bar_d + buf, n_d[buf]++ & 1);
         fence_after();
-        const uint32_t acc_col = buf ? COL_ACC1 : COL_ACC0;
+        const uint32_t acc_col = (buf ? COL_ACC1 : COL_ACC0) + 16 * half;
+        const int nst = (ncol + SROWS - 1) / SROWS;
 #pragma unroll 1
-        for (int s0 = 0; s0 < ncol; s0 += SUB) {
-          const int fbase = c * 128 + s0 + 8 * half;
-          uint32_t r[8];
-          tmem_ld8(tlane + acc_col + s0 + 8 * half, r);
-          const float* sx = nullptr;
+        for (int s = 0; s < nst; ++s) {
+          const int f0 = c * 128 + s * SROWS + 16 * half;
+          uint32_t r[16];
+          tmem_ld16(tlane + acc_col + s * SROWS, r);
+          const uint32_t* xv = nullptr;
           uint32_t slot = 0;
-          if (mode != MODE_WRITE) {
+          if (ENERGY) {
             slot = it % p.nstage;
             mbar_wait(bar_full + slot, (it / p.nstage) & 1);
             ++it;
-            sx = reinterpret_cast<const float*>(sRing + (size_t)slot * STAGE_BYTES) + (8 * half) * TM + row;
+            xv = reinterpret_cast<const uint32_t*>(sRing + (size_t)slot * STAGE_BYTES) + (16 * half) * TM + row;
+          }
+          float b3v[16];
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 t = *reinterpret_cast<const float4*>(sB3 + f0 + 4 * j4);
+            b3v[4 * j4] = t.x; b3v[4 * j4 + 1] = t.y; b3v[4 * j4 + 2] = t.z; b3v[4 * j4 + 3] = t.w;
           }
           tmem_ld_wait();
-          float ls = 0.f, rs = 0.f;
+          float sl = 0.f, sr = 0.f;
+          if (f0 + 16 <= F) {                              // full group: 8 pairs of bins
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int f = fbase + j;
-            if (f < F) {
-              const float vs = ex2_approx(fmaf(__uint_as_float(r[j]), W_SCALE_INV * LOG2E, sB3[f]));
-              if (mode != MODE_WRITE) {
-                const float x2 = sx[j * TM], vb = sx[(SUB + j) * TM];
-                const float vx = fmaf(g, vs, vb);
-                ls += lg2_approx(vx);
-                rs = fmaf(x2, rcp_approx(vx), rs);
+            for (int j = 0; j < 8; ++j) {
+              const float v0 = ex2_approx(fmaf(__uint_as_float(r[2 * j]), SC3, b3v[2 * j]));
+              const float v1 = ex2_approx(fmaf(__uint_as_float(r[2 * j + 1]), SC3, b3v[2 * j + 1]));
+              if (ENERGY) {
+                const uint32_t w0 = xv[(2 * j) * TM], w1 = xv[(2 * j + 1) * TM];
+                const float a = fmaf(g, v0, __uint_as_float(w0 << 16)), b = fmaf(g, v1, __uint_as_float(w1 << 16));
+                const float pr = a * b;
+                sl += lg2_approx(pr);
+                const float qn = fmaf(__uint_as_float(w0 & 0xffff0000u), b, __uint_as_float(w1 & 0xffff0000u) * a);
+                sr = fmaf(qn, rcp_approx(pr), sr);
               }
-              if (vs_out != nullptr && valid) vs_out[(size_t)f * NP + n] = vs;
+              if (STORE && valid) { vo[(size_t)(2 * j) * NP] = v0; vo[(size_t)(2 * j + 1) * NP] = v1; }
+            }
+          } else {                                         // ragged tail of the spectrum (F = 513: one bin)
+            const int nv = F - f0;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              if (j >= nv) break;
+              const float v0 = ex2_approx(fmaf(__uint_as_float(r[j]), SC3, b3v[j]));
+              if (ENERGY) {
+                const uint32_t w0 = xv[j * TM];
+                const float a = fmaf(g, v0, __uint_as_float(w0 << 16));
+                sl += lg2_approx(a);
+                sr = fmaf(__uint_as_float(w0 & 0xffff0000u), rcp_approx(a), sr);
+              }
+              if (STORE && valid) vo[(size_t)j * NP] = v0;
             }
           }
-          dl += (double)ls;
-          dr += (double)rs;
-          if (mode != MODE_WRITE) mbar_arrive(bar_empty + slot);
+          if (STORE) vo += (size_t)SROWS * NP;
+          if (ENERGY) {
+            dl += (double)sl;
+            dr += (double)sr;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_empty + slot);
+          }
         }
         fence_before();
-        mbar_arrive(bar_free + buf);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_free + buf);
       }
-      if (mode == MODE_WRITE) return 0.0;
-      sPart[tid] = dl * (double)LN2 + dr;
+      if (!ENERGY) return 0.0;
+      double* part = sPart + (n_dec & 1) * NE;
+      ++n_dec;
+      part[tid] = fma(dl, (double)LN2, dr);
       bar_epilogue();
-      const double e = sPart[row] + sPart[row + 128];
-      bar_epilogue();
-      return e;
+      return part[row] + part[row + 128];
     };
+    const std::true_type T{};
+    const std::false_type N{};
 
     // ---- chain ----
     if (half == 0) put_z(z);
-    Ct = decode(MODE_INIT, nullptr);
+    Ct = decode(T, N, nullptr);
+    int cur = 0;
+    float cnt = 0.f;
 
 #pragma unroll 1
     for (int m = 0; m < n_steps; ++m) {
@@ -323,8 +404,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_estep_tc(const __grid_constant_
         put_z(zp);
       }
       const int r = m - p.burnin;
-      float* spec = (r >= 1) ? p.Vs + (size_t)r * F * NP : nullptr;
-      const double Cp = decode(MODE_PROP, spec);
+      const double Cp = (r >= 1) ? decode(T, T, p.Vs + (size_t)r * F * NP) : decode(T, N, nullptr);
 
       // accept / reject (mcem.py:266-280)
       if (half == 0) {
@@ -353,30 +433,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_estep_tc(const __grid_constant_
 #pragma unroll
           for (int l = 0; l < L16; ++l) if (l < L) p.t_zs[((size_t)r * L + l) * NP + n] = z[l];
         }
-        if (r >= 1) sAcc[row] = ok;
+        // multiplicities of the kept samples (mcem.py:286-289: a rejected step repeats the state)
+        if (r == 0) { cur = 0; cnt = 1.f; }
+        else if (r >= 1) {
+          if (ok) { if (valid) p.Vs_w[(size_t)cur * NP + n] = cnt; cur = r; cnt = 1.f; }
+          else cnt += 1.f;
+        }
       }
-      // emit the kept sample (mcem.py:286-289 + compute_Vs)
+      // slot 0 holds the state after the burn-in: decode it once (mcem.py:286-289 + compute_Vs)
       if (r == 0) {
         if (half == 0) put_z(z);
-        decode(MODE_WRITE, p.Vs);
-      } else if (r >= 1) {
-        bar_epilogue();
-        if (valid && !sAcc[row]) {                 // rejected: the sample repeats the previous one
-          const float* prev = p.Vs + (size_t)(r - 1) * F * NP;
-          for (int f0 = 8 * half; f0 < F; f0 += 16) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int f = f0 + j;
-              if (f < F) spec[(size_t)f * NP + n] = prev[(size_t)f * NP + n];
-            }
-          }
-        }
-        bar_epilogue();
+        decode(N, T, p.Vs);
       }
     }
     if (half == 0 && valid) {
 #pragma unroll
       for (int l = 0; l < L16; ++l) if (l < L) p.Z[(size_t)l * NP + n] = z[l];
+      p.Vs_w[(size_t)cur * NP + n] = cnt;
       if (p.t_cnt != nullptr) p.t_cnt[n] += n_acc;
     }
   }
@@ -403,15 +476,15 @@ EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
-// [F][NP] f32 array, box = [SUB rows][128 frames]
-int32_t make_tile_map(CUtensorMap* m, const float* base, int F, int NP) {
+// [F][NP] u32 array, box = [SROWS rows][128 frames]
+int32_t make_tile_map(CUtensorMap* m, const uint32_t* base, int F, int NP) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (fn == nullptr) return fail(GVN_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t gdim[2] = {(cuuint64_t)NP, (cuuint64_t)F};
   cuuint64_t gstride[1] = {(cuuint64_t)NP * 4};
-  cuuint32_t box[2] = {(cuuint32_t)TM, (cuuint32_t)SUB};
+  cuuint32_t box[2] = {(cuuint32_t)TM, (cuuint32_t)SROWS};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<uint32_t*>(base), gdim, gstride, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(GVN_E_CUDA, "cuTensorMapEncodeTiled failed with %d", (int)r);
@@ -419,19 +492,19 @@ int32_t make_tile_map(CUtensorMap* m, const float* base, int F, int NP) {
 }
 
 template <int L16>
-int32_t launch_tc(const CUtensorMap& mx, const CUtensorMap& mv, const TcArgs& a, int grid, cudaStream_t st) {
-  const size_t fixed = (size_t)HID * L16 * 2 + (size_t)HID * HID * 2 + (size_t)a.FN * HID * 2 + (size_t)(a.FN + HID) * 4 +
-                       (size_t)NE * 8 + TM * 4 + (6 + 16) * 8 + 16;
+int32_t launch_tc(const CUtensorMap& mx, const TcArgs& a, int grid, cudaStream_t st) {
+  const size_t fixed = (size_t)HID * 2 * L16 * 2 + (size_t)HID * HID * 2 + (size_t)a.FN * HID * 2 + (size_t)(a.FN + 16 + HID) * 4 +
+                       (size_t)2 * NE * 8 + (7 + 2 * MAX_STAGES) * 8 + 16;
   TcArgs args = a;
   const size_t cap = 227 * 1024;
   int nstage = (int)((cap - fixed) / STAGE_BYTES);
-  if (nstage > 8) nstage = 8;
+  if (nstage > MAX_STAGES) nstage = MAX_STAGES;
   if (nstage < 2) return fail(GVN_E_UNSUPPORTED_SHAPE, "tensor-core E-step: shared memory does not fit (F=%d L=%d)", a.F, a.L);
   args.nstage = nstage;
   const size_t smem = fixed + (size_t)nstage * STAGE_BYTES;
   cudaError_t e = cudaFuncSetAttribute(k_estep_tc<L16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return fail(GVN_E_CUDA, "estep_tc smem attr (%zu B): %s", smem, cudaGetErrorString(e));
-  k_estep_tc<L16><<<grid, NTHREADS, smem, st>>>(mx, mv, args);
+  k_estep_tc<L16><<<grid, NTHREADS, smem, st>>>(mx, args);
   return check_launch("k_estep_tc");
 }
 
@@ -441,25 +514,30 @@ int32_t launch_estep_tc(const gvn_batch* b, const void* packed, int burnin, int 
                         const gvn_trace* tr, int precision, cudaStream_t st) {
   if (precision != GVN_PREC_F16)
     return fail(GVN_E_UNSUPPORTED_SHAPE, "precision %d: the hi/lo-split tensor-core chain is not built yet", precision);
+  GVN_REQUIRE(b->XV != nullptr && b->Vs_w != nullptr, GVN_E_INVALID, "batch.XV / batch.Vs_w is NULL");
   DecoderLayout d = decoder_layout(b->L, 0, b->F);
   TcLayout t = tc_layout(b->L, b->F);
   const unsigned char* base = reinterpret_cast<const unsigned char*>(packed);
-  CUtensorMap mx, mv;
-  int32_t rc = make_tile_map(&mx, b->X2, b->F, b->NP);
+  // per-launch constants of the chain: X2 and Vb as one bf16 pair per (f, frame)
+  const size_t n4 = (size_t)b->F * b->NP / 4;
+  k_pack_xv<<<148 * 8, 256, 0, st>>>(n4, reinterpret_cast<const float4*>(b->X2), reinterpret_cast<const float4*>(b->Vb),
+                                     reinterpret_cast<uint4*>(b->XV));
+  int32_t rc = check_launch("k_pack_xv");
   if (rc) return rc;
-  if ((rc = make_tile_map(&mv, b->Vb, b->F, b->NP))) return rc;
+  CUtensorMap mx;
+  if ((rc = make_tile_map(&mx, b->XV, b->F, b->NP))) return rc;
   TcArgs a;
   a.F = b->F; a.FN = t.FN; a.L = b->L; a.NP = b->NP; a.burnin = burnin; a.R = R; a.nstage = 0;
   a.sd = sqrtf(var_RW);
-  a.frame_utt = b->frame_utt; a.g = b->g; a.yproj = b->yproj; a.Z = b->Z; a.Vs = b->Vs;
-  a.img = base + d.tc_image; a.off_w1 = t.w1; a.off_w2 = t.w2; a.off_w3 = t.w3; a.off_b3s = t.b3s;
+  a.frame_utt = b->frame_utt; a.g = b->g; a.yproj = b->yproj; a.Z = b->Z; a.Vs = b->Vs; a.Vs_w = b->Vs_w;
+  a.img = base + d.tc_image; a.off_w1d = t.w1d; a.off_w2 = t.w2; a.off_w3 = t.w3; a.off_b3s = t.b3s;
   a.b2 = reinterpret_cast<const float*>(packed) + d.b2;
   a.eps = nz->eps; a.u = nz->u; a.forced = nz->forced_accept; a.seed = nz->seed; a.chain = nz->chain;
   a.t_acc = tr ? tr->acc_prob : nullptr; a.t_dec = tr ? tr->accepted : nullptr;
   a.t_cnt = tr ? tr->n_accepted : nullptr; a.t_zs = tr ? tr->z_samples : nullptr;
   const int grid = (b->NP + TM - 1) / TM;
-  if (t.L16 == 16) return launch_tc<16>(mx, mv, a, grid, st);
-  if (t.L16 == 32) return launch_tc<32>(mx, mv, a, grid, st);
+  if (t.L16 == 16) return launch_tc<16>(mx, a, grid, st);
+  if (t.L16 == 32) return launch_tc<32>(mx, a, grid, st);
   return fail(GVN_E_UNSUPPORTED_SHAPE, "tensor-core E-step supports L <= 32 (got %d)", b->L);
 }
 

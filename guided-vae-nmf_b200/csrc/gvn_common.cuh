@@ -39,6 +39,7 @@ struct TcLayout {
   int FN;                     // F rounded up to 16
   size_t w1, w2, w3;          // byte offsets (relative to tc_image) of the hi planes
   size_t plane_w1, plane_w2, plane_w3;   // bytes of one plane; lo plane follows hi plane
+  size_t w1d, plane_w1d;      // [128][2*L16] image of [W1 | W1] (A operand = z hi | z lo)
   size_t b1s, b3s;            // f32 vectors: (unused) / b3 * log2(e)
   size_t bytes;
 };
@@ -54,6 +55,8 @@ inline TcLayout tc_layout(int L, int F) {
   t.w1 = o; o += 2 * t.plane_w1;
   t.w2 = o; o += 2 * t.plane_w2;
   t.w3 = o; o += 2 * t.plane_w3;
+  t.plane_w1d = (size_t)GVN_HIDDEN * 2 * t.L16 * 2;
+  t.w1d = o; o += t.plane_w1d;
   o = round_up(o, 16);
   t.b1s = o; o += GVN_HIDDEN * 4;
   t.b3s = o; o += (size_t)t.FN * 4;

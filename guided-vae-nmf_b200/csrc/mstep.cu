@@ -25,9 +25,10 @@ constexpr int MS_WARPS = 8;
 template <int KMAX>
 __global__ void __launch_bounds__(256) k_mstep_w(int F, int K, int NP, int R, const int32_t* __restrict__ frame_off,
                                                  const int32_t* __restrict__ n_frames, const float* __restrict__ X2,
-                                                 const float* __restrict__ Vs, const float* __restrict__ Vb,
-                                                 const float* __restrict__ g, const float* __restrict__ H,
-                                                 const float* __restrict__ W, float* __restrict__ Wun) {
+                                                 const float* __restrict__ Vs, const float* __restrict__ Vs_w,
+                                                 const float* __restrict__ Vb, const float* __restrict__ g,
+                                                 const float* __restrict__ H, const float* __restrict__ W,
+                                                 float* __restrict__ Wun) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y, f = blockIdx.x * MS_WARPS + warp;
   if (f >= F) return;
@@ -45,9 +46,9 @@ __global__ void __launch_bounds__(256) k_mstep_w(int F, int K, int NP, int R, co
 #pragma unroll 5
     for (int r = 0; r < R; ++r) {
       float vx = fmaf(gg, vsp[(size_t)r * slab], vb);
-      float inv = 1.0f / vx;
-      s1 += inv;
-      s2 = fmaf(inv, inv, s2);
+      float inv = 1.0f / vx, wi = Vs_w[(size_t)r * NP + gn] * inv;     // slot multiplicity (gvn.h)
+      s1 += wi;
+      s2 = fmaf(wi, inv, s2);
     }
     const float a = x2 * s2;
 #pragma unroll
@@ -105,7 +106,7 @@ __global__ void __launch_bounds__(256) k_colnorm(int F, int K, const float* __re
 template <int KMAX>
 __global__ void __launch_bounds__(256) k_mstep_cols(int F, int K, int NP, int R, const int32_t* __restrict__ frame_utt,
                                                     const float* __restrict__ X2, const float* __restrict__ Vs,
-                                                    float* __restrict__ Vb, float* __restrict__ g, float* __restrict__ H,
+                                                    const float* __restrict__ Vs_w, float* __restrict__ Vb, float* __restrict__ g, float* __restrict__ H,
                                                     const float* __restrict__ Wun, const float* __restrict__ cnorm,
                                                     float* __restrict__ cost_part) {
   __shared__ float red[MS_WARPS][KMAX][MS_TILE];
@@ -135,9 +136,9 @@ __global__ void __launch_bounds__(256) k_mstep_cols(int F, int K, int NP, int R,
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll 5
     for (int r = 0; r < R; ++r) {
-      float inv = 1.0f / fmaf(gg, Vs[o + (size_t)r * slab], vb);
-      s1 += inv;
-      s2 = fmaf(inv, inv, s2);
+      float inv = 1.0f / fmaf(gg, Vs[o + (size_t)r * slab], vb), wi = Vs_w[(size_t)r * NP + gn] * inv;
+      s1 += wi;
+      s2 = fmaf(wi, inv, s2);
     }
     const float a = x2 * s2;
 #pragma unroll
@@ -181,9 +182,9 @@ __global__ void __launch_bounds__(256) k_mstep_cols(int F, int K, int NP, int R,
 #pragma unroll 5
     for (int r = 0; r < R; ++r) {
       float vs = Vs[o + (size_t)r * slab];
-      float inv = 1.0f / fmaf(gg, vs, vb);
-      t1 = fmaf(vs, inv, t1);
-      t2 = fmaf(vs * inv, inv, t2);
+      float inv = 1.0f / fmaf(gg, vs, vb), wv = Vs_w[(size_t)r * NP + gn] * vs;
+      t1 = fmaf(wv, inv, t1);
+      t2 = fmaf(wv * inv, inv, t2);
     }
     ng = fmaf(x2, t2, ng);
     dg += t1;
@@ -207,7 +208,7 @@ __global__ void __launch_bounds__(256) k_mstep_cols(int F, int K, int NP, int R,
 #pragma unroll 5
       for (int r = 0; r < R; ++r) {
         float vx = fmaf(gnew, Vs[o + (size_t)r * slab], vb);
-        c += logf(vx) + x2 / vx;
+        c = fmaf(Vs_w[(size_t)r * NP + gn], logf(vx) + x2 / vx, c);
       }
       cs += c;
     }
@@ -243,8 +244,9 @@ __global__ void k_cost_reduce(int B, int F, int R, int niter, int ntiles, const 
 
 // ------------------------------------------------------------ Wiener (mcem.py:341-343, :175-176)
 __global__ void __launch_bounds__(256) k_wiener(int F, int NP, int R, const int32_t* __restrict__ frame_utt,
-                                                const float* __restrict__ Vs, const float* __restrict__ Vb,
-                                                const float* __restrict__ g, const float2* __restrict__ Xc,
+                                                const float* __restrict__ Vs, const float* __restrict__ Vs_w,
+                                                const float* __restrict__ Vb, const float* __restrict__ g,
+                                                const float2* __restrict__ Xc,
                                                 float2* __restrict__ S_hat, float2* __restrict__ N_hat,
                                                 float* __restrict__ WFs, float* __restrict__ WFn) {
   const size_t total = (size_t)F * NP, slab = total;
@@ -254,10 +256,10 @@ __global__ void __launch_bounds__(256) k_wiener(int F, int NP, int R, const int3
     if (frame_utt[gn] >= 0) {
       const float gg = g[gn], vb = Vb[i];
       for (int r = 0; r < R; ++r) {
-        float sc = gg * Vs[i + (size_t)r * slab];
+        float sc = gg * Vs[i + (size_t)r * slab], w = Vs_w[(size_t)r * NP + gn];
         float vx = sc + vb;
-        ws += sc / vx;
-        wn += vb / vx;
+        ws = fmaf(w, sc / vx, ws);
+        wn = fmaf(w, vb / vx, wn);
       }
       ws /= (float)R;
       wn /= (float)R;
@@ -316,10 +318,10 @@ int32_t launch_mstep(const gvn_batch* b, int R, float* cost_part, void* workspac
   dim3 gw((b->F + MS_WARPS - 1) / MS_WARPS, b->B);
   const int ntiles = b->NP / MS_TILE;
   if (b->K <= 16) {
-    k_mstep_w<16><<<gw, 256, 0, st>>>(b->F, b->K, b->NP, R, b->frame_off, b->n_frames, b->X2, b->Vs, b->Vb, b->g,
+    k_mstep_w<16><<<gw, 256, 0, st>>>(b->F, b->K, b->NP, R, b->frame_off, b->n_frames, b->X2, b->Vs, b->Vs_w, b->Vb, b->g,
                                        b->H, b->W, b->Wun);
   } else {
-    k_mstep_w<32><<<gw, 256, 0, st>>>(b->F, b->K, b->NP, R, b->frame_off, b->n_frames, b->X2, b->Vs, b->Vb, b->g,
+    k_mstep_w<32><<<gw, 256, 0, st>>>(b->F, b->K, b->NP, R, b->frame_off, b->n_frames, b->X2, b->Vs, b->Vs_w, b->Vb, b->g,
                                        b->H, b->W, b->Wun);
   }
   int32_t rc = check_launch("k_mstep_w");
@@ -327,10 +329,10 @@ int32_t launch_mstep(const gvn_batch* b, int R, float* cost_part, void* workspac
   k_colnorm<<<b->B, 256, 0, st>>>(b->F, b->K, b->Wun, b->W, cnorm);
   if ((rc = check_launch("k_colnorm"))) return rc;
   if (b->K <= 16) {
-    k_mstep_cols<16><<<ntiles, 256, 0, st>>>(b->F, b->K, b->NP, R, b->frame_utt, b->X2, b->Vs, b->Vb, b->g, b->H,
+    k_mstep_cols<16><<<ntiles, 256, 0, st>>>(b->F, b->K, b->NP, R, b->frame_utt, b->X2, b->Vs, b->Vs_w, b->Vb, b->g, b->H,
                                              b->Wun, cnorm, cost_part);
   } else {
-    k_mstep_cols<32><<<ntiles, 256, 0, st>>>(b->F, b->K, b->NP, R, b->frame_utt, b->X2, b->Vs, b->Vb, b->g, b->H,
+    k_mstep_cols<32><<<ntiles, 256, 0, st>>>(b->F, b->K, b->NP, R, b->frame_utt, b->X2, b->Vs, b->Vs_w, b->Vb, b->g, b->H,
                                              b->Wun, cnorm, cost_part);
   }
   return check_launch("k_mstep_cols");
@@ -347,7 +349,7 @@ int32_t launch_wiener(const gvn_batch* b, int R, float* S_hat, float* N_hat, flo
   size_t total = (size_t)b->F * b->NP;
   int grid = (int)((total + 255) / 256);
   if (grid > 148 * 16) grid = 148 * 16;
-  k_wiener<<<grid, 256, 0, st>>>(b->F, b->NP, R, b->frame_utt, b->Vs, b->Vb, b->g,
+  k_wiener<<<grid, 256, 0, st>>>(b->F, b->NP, R, b->frame_utt, b->Vs, b->Vs_w, b->Vb, b->g,
                                  reinterpret_cast<const float2*>(b->Xc), reinterpret_cast<float2*>(S_hat),
                                  reinterpret_cast<float2*>(N_hat), WFs, WFn);
   return check_launch("k_wiener");

@@ -4,20 +4,19 @@
 // of :68-70); what changes is how the (R,F,N) block of speech variances moves:
 //
 //   k_w_v1     W update (mcem.py:105-110).  One warp per (utterance, frequency row), float4
-//              loads of ten Vs planes + X2 + Vb per lane in flight, H through L1, one pass.
+//              loads of all R sample slots + X2 + Vb per lane in flight, H through L1, one pass.
 //   k_cols_v1  H update, refresh, normalisation, g update and cost (mcem.py:113-152, :68-70)
 //              as ONE sweep: a persistent CTA owns a contiguous range of 8-frame column tiles;
-//              the whole (R+1) x F x 8 block of a tile (Vs planes + X2) is staged ONCE in
-//              shared memory by 16-byte async copies (row segments of 32 B; the L2::128B
-//              prefetch hint pulls the full line, which the next three tiles of the same CTA
-//              hit in L2) and the three dependent passes (H | g | cost) run out of shared
-//              memory.  The copy of tile t+1 is issued chunk by chunk behind the cost pass of
-//              tile t and the H pass of tile t+1 chases the arriving chunks, so loads are in
-//              flight during two of the three passes.
+//              the whole F x (R+1) x 8 block of a tile (Vs slots + X2) is staged ONCE in shared
+//              memory by 16-byte async copies and the three dependent passes (H | g | cost) run
+//              out of shared memory.  The copy of the next tile is issued chunk by chunk behind
+//              the cost pass of the current one and the H pass of the next tile chases the
+//              arriving chunks, so loads are in flight during two of the three passes.
 //
-// Transcendental budget: 1/a + 1/b = (a+b)/(ab) and log a + log b = log(ab) turn the two MUFU
-// operations per element and pass into one per PAIR of samples (Vx >= K*eps^2 ~ 1e-15, so the
-// product of two stays far inside the fp32 range).
+// The samples arrive in slot form (Vs, Vs_w: include/gvn.h): every sum over the R samples of the
+// reference is a multiplicity-weighted sum over the R slots.
+// Transcendental budget: 1/a and 1/c of a pair of slots come from ONE reciprocal of the product
+// (1/a = c * rcp(ac)); Vx >= K*eps^2 ~ 1e-15, so the product stays far inside the fp32 range.
 #include "gvn_common.cuh"
 
 namespace gvn {
@@ -30,7 +29,7 @@ constexpr int MAXCH = 8;              // load chunks per tile
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void cp16(void* dst, const void* src) {
-  asm volatile("cp.async.cg.shared.global.L2::128B [%0], [%1], 16;" ::"r"(s_u32(dst)), "l"(src) : "memory");
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s_u32(dst)), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_wait_dyn(int pending) {
@@ -53,27 +52,32 @@ __device__ __forceinline__ float4 ldg_stream4(const float* p) {
   return v;
 }
 
-// ------------------------------------------------------------------ W update (mcem.py:105-110)
-// sums of one pair of samples for four adjacent frames
-__device__ __forceinline__ void pair_acc(float g, float vb, float va, float vc, float& s1, float& s2) {
+// weighted sums  s1 += wa/a + wc/c,  s2 += wa/a^2 + wc/c^2  with a = g*va + vb, c = g*vc + vb
+__device__ __forceinline__ void pair_acc(float g, float vb, float va, float vc, float wa, float wc, float& s1, float& s2) {
   const float a = fmaf(g, va, vb), c = fmaf(g, vc, vb);
   const float ip = rcp_fast(a * c);
   const float ia = c * ip, ic = a * ip;          // 1/a, 1/c
-  s1 += ia + ic;
-  s2 = fmaf(ia, ia, fmaf(ic, ic, s2));
+  const float ta = wa * ia, tc = wc * ic;
+  s1 += ta;
+  s1 += tc;
+  s2 = fmaf(ta, ia, s2);
+  s2 = fmaf(tc, ic, s2);
 }
-__device__ __forceinline__ void single_acc(float g, float vb, float va, float& s1, float& s2) {
-  const float ia = rcp_fast(fmaf(g, va, vb));
-  s1 += ia;
-  s2 = fmaf(ia, ia, s2);
+__device__ __forceinline__ void single_acc(float g, float vb, float va, float wa, float& s1, float& s2) {
+  const float ia = rcp_fast(fmaf(g, va, vb)), ta = wa * ia;
+  s1 += ta;
+  s2 = fmaf(ta, ia, s2);
 }
 
-template <int KMAX>
-__global__ void __launch_bounds__(CT) k_w_v1(int F, int K, int NP, int R, const int32_t* __restrict__ frame_off,
+// ------------------------------------------------------------------ W update (mcem.py:105-110)
+template <int KMAX, int RT>
+__global__ void __launch_bounds__(CT) k_w_v1(int F, int K, int NP, int R_rt, const int32_t* __restrict__ frame_off,
                                              const int32_t* __restrict__ n_frames, const float* __restrict__ X2,
-                                             const float* __restrict__ Vs, const float* __restrict__ Vb,
-                                             const float* __restrict__ g, const float* __restrict__ H,
-                                             const float* __restrict__ W, float* __restrict__ Wun) {
+                                             const float* __restrict__ Vs, const float* __restrict__ Vs_w,
+                                             const float* __restrict__ Vb, const float* __restrict__ g,
+                                             const float* __restrict__ H, const float* __restrict__ W,
+                                             float* __restrict__ Wun) {
+  const int R = RT > 0 ? RT : R_rt;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y, f = blockIdx.x * (CT / 32) + warp;
   if (f >= F) return;
@@ -85,24 +89,51 @@ __global__ void __launch_bounds__(CT) k_w_v1(int F, int K, int NP, int R, const 
   const size_t row = (size_t)f * NP, slab = (size_t)F * NP;
   for (int n4 = lane * 4; n4 < NPAD; n4 += 128) {
     const size_t o = row + n_begin + n4;
+    const float* vsp = Vs + o;
+    const float* wp = Vs_w + n_begin + n4;
     const float4 vb = ldg_stream4(Vb + o), x2 = ldg_stream4(X2 + o);
     const float4 gg = __ldg(reinterpret_cast<const float4*>(g + n_begin + n4));
     float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
-    int r = 0;
-#pragma unroll 5
-    for (; r + 1 < R; r += 2) {
-      const float4 va = ldg_stream4(Vs + o + (size_t)r * slab), vc = ldg_stream4(Vs + o + (size_t)(r + 1) * slab);
-      pair_acc(gg.x, vb.x, va.x, vc.x, s1.x, s2.x);
-      pair_acc(gg.y, vb.y, va.y, vc.y, s1.y, s2.y);
-      pair_acc(gg.z, vb.z, va.z, vc.z, s1.z, s2.z);
-      pair_acc(gg.w, vb.w, va.w, vc.w, s1.w, s2.w);
-    }
-    if (r < R) {
-      const float4 va = ldg_stream4(Vs + o + (size_t)r * slab);
-      single_acc(gg.x, vb.x, va.x, s1.x, s2.x);
-      single_acc(gg.y, vb.y, va.y, s1.y, s2.y);
-      single_acc(gg.z, vb.z, va.z, s1.z, s2.z);
-      single_acc(gg.w, vb.w, va.w, s1.w, s2.w);
+    if (RT > 0) {
+      float4 v[RT > 0 ? RT : 1];
+#pragma unroll
+      for (int r = 0; r < RT; ++r) v[r] = ldg_stream4(vsp + (size_t)r * slab);     // all slots in flight
+#pragma unroll
+      for (int r = 0; r + 1 < RT; r += 2) {
+        const float4 wa = __ldg(reinterpret_cast<const float4*>(wp + (size_t)r * NP));
+        const float4 wc = __ldg(reinterpret_cast<const float4*>(wp + (size_t)(r + 1) * NP));
+        pair_acc(gg.x, vb.x, v[r].x, v[r + 1].x, wa.x, wc.x, s1.x, s2.x);
+        pair_acc(gg.y, vb.y, v[r].y, v[r + 1].y, wa.y, wc.y, s1.y, s2.y);
+        pair_acc(gg.z, vb.z, v[r].z, v[r + 1].z, wa.z, wc.z, s1.z, s2.z);
+        pair_acc(gg.w, vb.w, v[r].w, v[r + 1].w, wa.w, wc.w, s1.w, s2.w);
+      }
+      if (RT & 1) {
+        const float4 wa = __ldg(reinterpret_cast<const float4*>(wp + (size_t)(RT - 1) * NP));
+        single_acc(gg.x, vb.x, v[RT - 1].x, wa.x, s1.x, s2.x);
+        single_acc(gg.y, vb.y, v[RT - 1].y, wa.y, s1.y, s2.y);
+        single_acc(gg.z, vb.z, v[RT - 1].z, wa.z, s1.z, s2.z);
+        single_acc(gg.w, vb.w, v[RT - 1].w, wa.w, s1.w, s2.w);
+      }
+    } else {
+      int r = 0;
+#pragma unroll 2
+      for (; r + 1 < R; r += 2) {
+        const float4 va = ldg_stream4(vsp + (size_t)r * slab), vc = ldg_stream4(vsp + (size_t)(r + 1) * slab);
+        const float4 wa = __ldg(reinterpret_cast<const float4*>(wp + (size_t)r * NP));
+        const float4 wc = __ldg(reinterpret_cast<const float4*>(wp + (size_t)(r + 1) * NP));
+        pair_acc(gg.x, vb.x, va.x, vc.x, wa.x, wc.x, s1.x, s2.x);
+        pair_acc(gg.y, vb.y, va.y, vc.y, wa.y, wc.y, s1.y, s2.y);
+        pair_acc(gg.z, vb.z, va.z, vc.z, wa.z, wc.z, s1.z, s2.z);
+        pair_acc(gg.w, vb.w, va.w, vc.w, wa.w, wc.w, s1.w, s2.w);
+      }
+      if (r < R) {
+        const float4 va = ldg_stream4(vsp + (size_t)r * slab);
+        const float4 wa = __ldg(reinterpret_cast<const float4*>(wp + (size_t)r * NP));
+        single_acc(gg.x, vb.x, va.x, wa.x, s1.x, s2.x);
+        single_acc(gg.y, vb.y, va.y, wa.y, s1.y, s2.y);
+        single_acc(gg.z, vb.z, va.z, wa.z, s1.z, s2.z);
+        single_acc(gg.w, vb.w, va.w, wa.w, s1.w, s2.w);
+      }
     }
     float4 a = make_float4(x2.x * s2.x, x2.y * s2.y, x2.z * s2.z, x2.w * s2.w);
     // frames beyond the utterance (padding up to the 32-frame boundary) contribute nothing
@@ -140,34 +171,35 @@ __global__ void __launch_bounds__(CT) k_w_v1(int F, int K, int NP, int R, const 
 
 // ------------------------------------------- column sweep: H, Vb, normalisation, g, cost
 struct ColsArgs {
-  int F, K, KS, NP, R, B, ntiles, nchunk;
+  int F, K, KS, NP, R, RS, B, ntiles, nchunk;
   const int32_t* frame_utt; const int32_t* frame_off;
-  const float* X2; const float* Vs;
+  const float* X2; const float* Vs; const float* Vs_w;
   float* Vb; float* g; float* H; const float* Wun; float* W; float* cost_part;
 };
 
-// shared-memory carve-up (floats): data[(R+1)][F][NB] | W_s[F][KS] | small arrays
-struct ColsSmem {
-  float* data; float* W_s; float* red; float* red2; float* Hn_s; float* meta; float* cn_s; float* misc;
-};
-__host__ __device__ inline size_t cols_smem_floats(int F, int KS, int R, int KMAX) {
-  return (size_t)(R + 1) * F * NB + (size_t)F * KS + (size_t)8 * 2 * KMAX * NB + (size_t)2 * KMAX * NB + (size_t)KMAX * NB +
-         (size_t)(KMAX + 2) * NB + KMAX + 32;
+// shared memory (floats): data[F][RS][NB] (slot r of bin f at [f][r], X2 at [f][R]) | W_s[F][KS] |
+// red[8][2*KMAX][NB] | red2[2*KMAX][NB] | Hn_s[KMAX][NB] | meta[(KMAX+2+R)][NB] | wts_s[R][NB] | cn_s[KMAX] | misc[32]
+__host__ __device__ inline size_t cols_smem_floats(int F, int KS, int R, int RS, int KMAX) {
+  return (size_t)F * RS * NB + (size_t)F * KS + (size_t)8 * 2 * KMAX * NB + (size_t)2 * KMAX * NB + (size_t)KMAX * NB +
+         (size_t)(KMAX + 2 + R) * NB + (size_t)R * NB + KMAX + 32;
 }
 
-template <int KMAX>
+template <int KMAX, int RT>
 __global__ void __launch_bounds__(CT, 1) k_cols_v1(ColsArgs p) {
   extern __shared__ __align__(16) float sm[];
-  const int F = p.F, K = p.K, KS = p.KS, NP = p.NP, R = p.R;
-  const int PS = F * NB;                                    // plane stride (floats)
-  float* data = sm;                                         // [(R+1)][F][NB]; plane R = X2
-  float* W_s = data + (size_t)(R + 1) * PS;                 // [F][KS]
-  float* red = W_s + (size_t)F * KS;                        // [8 warps][2*KMAX][NB]
-  float* red2 = red + 8 * 2 * KMAX * NB;                    // [2*KMAX][NB]
-  float* Hn_s = red2 + 2 * KMAX * NB;                       // [KMAX][NB]
-  float* meta = Hn_s + KMAX * NB;                           // H_old [KMAX][NB] | g [NB] | frame_utt [NB] (int bits)
-  float* cn_s = meta + (KMAX + 2) * NB;                     // [KMAX] column norms of W
-  float* misc = cn_s + KMAX;                                // [32]
+  const int F = p.F, K = p.K, KS = p.KS, NP = p.NP;
+  const int R = RT > 0 ? RT : p.R;
+  const int RS = RT > 0 ? ((RT + 1) | 1) : p.RS;            // row stride in 8-float groups (odd: conflict-free)
+  const int FS = RS * NB;                                   // floats per frequency row
+  float* data = sm;
+  float* W_s = data + (size_t)F * FS;
+  float* red = W_s + (size_t)F * KS;
+  float* red2 = red + 8 * 2 * KMAX * NB;
+  float* Hn_s = red2 + 2 * KMAX * NB;
+  float* meta = Hn_s + KMAX * NB;                           // H_old [KMAX][NB] | g [NB] | frame_utt [NB] | Vs_w [R][NB]
+  float* wts_s = meta + (KMAX + 2 + R) * NB;                // [R][NB] multiplicities of the current tile
+  float* cn_s = wts_s + R * NB;
+  float* misc = cn_s + KMAX;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n = tid & (NB - 1), fl = tid >> 3;              // column of the tile, frequency lane (0..31)
@@ -187,23 +219,23 @@ __global__ void __launch_bounds__(CT, 1) k_cols_v1(ColsArgs p) {
     const int rows2 = (r1 - r0) * 2;
     const size_t col = (size_t)t * NB;
     const int total = rows2 * (R + 1);
-    if (rows2 == 128) {
-      for (int q = tid; q < total; q += CT) {
-        const int plane = q >> 7, rem = q & 127, rowi = r0 + (rem >> 1), half = rem & 1;
-        const float* src = (plane < R ? p.Vs + ((size_t)plane * F + rowi) * NP : p.X2 + (size_t)rowi * NP) + col + 4 * half;
-        cp16(data + (size_t)plane * PS + rowi * NB + 4 * half, src);
-      }
-    } else {
-      for (int q = tid; q < total; q += CT) {
-        const int plane = q / rows2, rem = q - plane * rows2, rowi = r0 + (rem >> 1), half = rem & 1;
-        const float* src = (plane < R ? p.Vs + ((size_t)plane * F + rowi) * NP : p.X2 + (size_t)rowi * NP) + col + 4 * half;
-        cp16(data + (size_t)plane * PS + rowi * NB + 4 * half, src);
-      }
+    const bool pow2 = rows2 == 128;
+    for (int q = tid; q < total; q += CT) {
+      const int plane = pow2 ? (q >> 7) : q / rows2;
+      const int rem = pow2 ? (q & 127) : q - plane * rows2;
+      const int rowi = r0 + (rem >> 1), half = rem & 1;
+      const float* src = (plane < R ? p.Vs + ((size_t)plane * F + rowi) * NP : p.X2 + (size_t)rowi * NP) + col + 4 * half;
+      cp16(data + (size_t)rowi * FS + plane * NB + 4 * half, src);
     }
-    if (j == 0) {   // tile meta data: H_old rows, g, frame_utt
-      if (tid < 2 * K) cp16(meta + (tid >> 1) * NB + 4 * (tid & 1), p.H + (size_t)(tid >> 1) * NP + col + 4 * (tid & 1));
-      else if (tid < 2 * K + 2) cp16(meta + KMAX * NB + 4 * (tid - 2 * K), p.g + col + 4 * (tid - 2 * K));
-      else if (tid < 2 * K + 4) cp16(meta + (KMAX + 1) * NB + 4 * (tid - 2 * K - 2), p.frame_utt + col + 4 * (tid - 2 * K - 2));
+    if (j == 0) {   // tile meta data: H_old rows, g, frame_utt, slot multiplicities
+      const int nH = 2 * K, nW = 2 * R;
+      if (tid < nH) cp16(meta + (tid >> 1) * NB + 4 * (tid & 1), p.H + (size_t)(tid >> 1) * NP + col + 4 * (tid & 1));
+      else if (tid < nH + 2) cp16(meta + KMAX * NB + 4 * (tid - nH), p.g + col + 4 * (tid - nH));
+      else if (tid < nH + 4) cp16(meta + (KMAX + 1) * NB + 4 * (tid - nH - 2), p.frame_utt + col + 4 * (tid - nH - 2));
+      else if (tid < nH + 4 + nW) {
+        const int q = tid - nH - 4;
+        cp16(meta + (KMAX + 2 + (q >> 1)) * NB + 4 * (q & 1), p.Vs_w + (size_t)(q >> 1) * NP + col + 4 * (q & 1));
+      }
     }
     cp_commit();
   };
@@ -228,6 +260,17 @@ __global__ void __launch_bounds__(CT, 1) k_cols_v1(ColsArgs p) {
     float hk[KMAX];
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) hk[k] = (k < K) ? meta[k * NB + n] : 0.f;
+    // multiplicities of the slots of this column: registers when R is a compile-time constant,
+    // a private shared copy otherwise (`meta` is overwritten by the next tile's copies)
+    float wr[RT > 0 ? RT : 1];
+    if (RT > 0) {
+#pragma unroll
+      for (int r = 0; r < RT; ++r) wr[r] = meta[(KMAX + 2 + r) * NB + n];
+    } else {
+      for (int i = tid; i < R * NB; i += CT) wts_s[i] = meta[(KMAX + 2) * NB + i];
+    }
+    const float* wsm = wts_s + n;
+    auto wgt = [&](int r) -> float { return RT > 0 ? wr[RT > 0 ? r : 0] : wsm[r * NB]; };
 
     if (b != cur_b) {                                       // new utterance: dictionary -> smem, column norms
       cur_b = b;
@@ -243,8 +286,8 @@ __global__ void __launch_bounds__(CT, 1) k_cols_v1(ColsArgs p) {
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         if (lane == 0) cn_s[k] = s;
       }
-      __syncthreads();
     }
+    __syncthreads();                                        // W_s, cn_s, wts_s visible
     if (t * NB == cur_fo) {                                 // the first tile of an utterance writes W / c (mcem.py:131)
       float* wdst = p.W + (size_t)b * F * K;
       for (int i = tid; i < F * K; i += CT) { const int ff = i / K, k = i - ff * K; wdst[i] = W_s[ff * KS + k] / cn_s[k]; }
@@ -257,25 +300,30 @@ __global__ void __launch_bounds__(CT, 1) k_cols_v1(ColsArgs p) {
     for (int j = 0; j < NCH; ++j) {
       if (j > 0) { cp_wait_dyn(NCH - 1 - j); __syncthreads(); }
       const int i0 = j * NI / NCH, i1 = (j + 1) * NI / NCH;
-      for (int i = i0; i < i1; ++i) {
-        const int f = i * 32 + fl;
-        if (f < F) {
+      const float* vs = data + (size_t)(i0 * 32 + fl) * FS + n;
+      const float* wrow = W_s + (i0 * 32 + fl) * KS;
+      for (int i = i0; i < i1; ++i, vs += 32 * FS, wrow += 32 * KS) {
+        if (i * 32 + fl < F) {
           float w[KMAX];
 #pragma unroll
           for (int k4 = 0; k4 < KMAX; k4 += 4) {
-            const float4 t4 = *reinterpret_cast<const float4*>(W_s + f * KS + k4);
+            const float4 t4 = *reinterpret_cast<const float4*>(wrow + k4);
             w[k4] = t4.x; w[k4 + 1] = t4.y; w[k4 + 2] = t4.z; w[k4 + 3] = t4.w;
           }
           float vb = 0.f;
 #pragma unroll
           for (int k = 0; k < KMAX; ++k) vb = fmaf(w[k], hk[k], vb);
-          const float* vs = data + f * NB + n;
           float s1 = 0.f, s2 = 0.f;
-          int r = 0;
-#pragma unroll 5
-          for (; r + 1 < R; r += 2) pair_acc(gg, vb, vs[(size_t)r * PS], vs[(size_t)(r + 1) * PS], s1, s2);
-          if (r < R) single_acc(gg, vb, vs[(size_t)r * PS], s1, s2);
-          const float a = vs[(size_t)R * PS] * s2;
+          if (RT > 0) {
+#pragma unroll
+            for (int r = 0; r + 1 < RT; r += 2) pair_acc(gg, vb, vs[r * NB], vs[(r + 1) * NB], wgt(r), wgt(r + 1), s1, s2);
+            if (RT & 1) single_acc(gg, vb, vs[(RT - 1) * NB], wgt(RT - 1), s1, s2);
+          } else {
+            int r = 0;
+            for (; r + 1 < R; r += 2) pair_acc(gg, vb, vs[r * NB], vs[(r + 1) * NB], wgt(r), wgt(r + 1), s1, s2);
+            if (r < R) single_acc(gg, vb, vs[r * NB], wgt(r), s1, s2);
+          }
+          const float a = vs[R * NB] * s2;
 #pragma unroll
           for (int k = 0; k < KMAX; ++k) { num[k] = fmaf(w[k], a, num[k]); den[k] = fmaf(w[k], s1, den[k]); }
         }
@@ -315,37 +363,47 @@ __global__ void __launch_bounds__(CT, 1) k_cols_v1(ColsArgs p) {
 
     // ---------------- pass B: Vb = Wun @ H_new (kept for the next E-step, mcem.py:124); g update (:138-142)
     float ng = 0.f, dg = 0.f;
-    for (int i = 0; i < NI; ++i) {
-      const int f = i * 32 + fl;
-      if (f < F) {
-        float vb = 0.f;
+    {
+      const float* vs = data + (size_t)fl * FS + n;
+      const float* wrow = W_s + fl * KS;
+      float* vbo = p.Vb + (size_t)fl * NP + (size_t)t * NB + n;
+      for (int i = 0; i < NI; ++i, vs += 32 * FS, wrow += 32 * KS, vbo += (size_t)32 * NP) {
+        if (i * 32 + fl < F) {
+          float vb = 0.f;
 #pragma unroll
-        for (int k4 = 0; k4 < KMAX; k4 += 4) {
-          const float4 t4 = *reinterpret_cast<const float4*>(W_s + f * KS + k4);
-          vb = fmaf(t4.x, hn[k4], fmaf(t4.y, hn[k4 + 1], fmaf(t4.z, hn[k4 + 2], fmaf(t4.w, hn[k4 + 3], vb))));
+          for (int k4 = 0; k4 < KMAX; k4 += 4) {
+            const float4 t4 = *reinterpret_cast<const float4*>(wrow + k4);
+            vb = fmaf(t4.x, hn[k4], fmaf(t4.y, hn[k4 + 1], fmaf(t4.z, hn[k4 + 2], fmaf(t4.w, hn[k4 + 3], vb))));
+          }
+          if (valid) *vbo = vb;
+          float t1 = 0.f, t2 = 0.f;
+          auto pairB = [&](float va, float vc, float wa, float wc) {
+            const float a = fmaf(gg, va, vb), c = fmaf(gg, vc, vb);
+            const float ip = rcp_fast(a * c);
+            const float ia = c * ip, ic = a * ip;
+            const float ua = wa * va * ia, uc = wc * vc * ic;
+            t1 += ua;
+            t1 += uc;
+            t2 = fmaf(ua, ia, t2);
+            t2 = fmaf(uc, ic, t2);
+          };
+          auto singleB = [&](float va, float wa) {
+            const float ia = rcp_fast(fmaf(gg, va, vb)), ua = wa * va * ia;
+            t1 += ua;
+            t2 = fmaf(ua, ia, t2);
+          };
+          if (RT > 0) {
+#pragma unroll
+            for (int r = 0; r + 1 < RT; r += 2) pairB(vs[r * NB], vs[(r + 1) * NB], wgt(r), wgt(r + 1));
+            if (RT & 1) singleB(vs[(RT - 1) * NB], wgt(RT - 1));
+          } else {
+            int r = 0;
+            for (; r + 1 < R; r += 2) pairB(vs[r * NB], vs[(r + 1) * NB], wgt(r), wgt(r + 1));
+            if (r < R) singleB(vs[r * NB], wgt(r));
+          }
+          ng = fmaf(vs[R * NB], t2, ng);
+          dg += t1;
         }
-        if (valid) p.Vb[(size_t)f * NP + (size_t)t * NB + n] = vb;
-        const float* vs = data + f * NB + n;
-        float t1 = 0.f, t2 = 0.f;
-        int r = 0;
-#pragma unroll 5
-        for (; r + 1 < R; r += 2) {
-          const float va = vs[(size_t)r * PS], vc = vs[(size_t)(r + 1) * PS];
-          const float a = fmaf(gg, va, vb), c = fmaf(gg, vc, vb);
-          const float ip = rcp_fast(a * c);
-          const float ia = c * ip, ic = a * ip;
-          const float ua = va * ia, uc = vc * ic;
-          t1 += ua + uc;
-          t2 = fmaf(ua, ia, fmaf(uc, ic, t2));
-        }
-        if (r < R) {
-          const float va = vs[(size_t)r * PS];
-          const float ia = rcp_fast(fmaf(gg, va, vb)), ua = va * ia;
-          t1 += ua;
-          t2 = fmaf(ua, ia, t2);
-        }
-        ng = fmaf(vs[(size_t)R * PS], t2, ng);
-        dg += t1;
       }
     }
     ng += __shfl_xor_sync(0xffffffffu, ng, 8);
@@ -369,32 +427,39 @@ __global__ void __launch_bounds__(CT, 1) k_cols_v1(ColsArgs p) {
     float cl = 0.f, cr = 0.f;
     for (int j = 0; j < NCH; ++j) {
       const int i0 = j * NI / NCH, i1 = (j + 1) * NI / NCH;
-      for (int i = i0; i < i1; ++i) {
-        const int f = i * 32 + fl;
-        if (f < F) {
+      const float* vs = data + (size_t)(i0 * 32 + fl) * FS + n;
+      const float* wrow = W_s + (i0 * 32 + fl) * KS;
+      for (int i = i0; i < i1; ++i, vs += 32 * FS, wrow += 32 * KS) {
+        if (i * 32 + fl < F) {
           float vb = 0.f;
 #pragma unroll
           for (int k4 = 0; k4 < KMAX; k4 += 4) {
-            const float4 t4 = *reinterpret_cast<const float4*>(W_s + f * KS + k4);
+            const float4 t4 = *reinterpret_cast<const float4*>(wrow + k4);
             vb = fmaf(t4.x, hn[k4], fmaf(t4.y, hn[k4 + 1], fmaf(t4.z, hn[k4 + 2], fmaf(t4.w, hn[k4 + 3], vb))));
           }
-          const float* vs = data + f * NB + n;
           float sl = 0.f, sr = 0.f;
-          int r = 0;
-#pragma unroll 5
-          for (; r + 1 < R; r += 2) {
-            const float a = fmaf(gnew, vs[(size_t)r * PS], vb), c = fmaf(gnew, vs[(size_t)(r + 1) * PS], vb);
-            const float pr = a * c;
-            sl += lg2_fast(pr);
-            sr = fmaf(a + c, rcp_fast(pr), sr);
-          }
-          if (r < R) {
-            const float a = fmaf(gnew, vs[(size_t)r * PS], vb);
-            sl += lg2_fast(a);
-            sr += rcp_fast(a);
+          auto pairC = [&](float va, float vc, float wa, float wc) {
+            const float a = fmaf(gnew, va, vb), c = fmaf(gnew, vc, vb);
+            sl = fmaf(wa, lg2_fast(a), sl);
+            sl = fmaf(wc, lg2_fast(c), sl);
+            sr = fmaf(fmaf(wa, c, wc * a), rcp_fast(a * c), sr);
+          };
+          auto singleC = [&](float va, float wa) {
+            const float a = fmaf(gnew, va, vb);
+            sl = fmaf(wa, lg2_fast(a), sl);
+            sr = fmaf(wa, rcp_fast(a), sr);
+          };
+          if (RT > 0) {
+#pragma unroll
+            for (int r = 0; r + 1 < RT; r += 2) pairC(vs[r * NB], vs[(r + 1) * NB], wgt(r), wgt(r + 1));
+            if (RT & 1) singleC(vs[(RT - 1) * NB], wgt(RT - 1));
+          } else {
+            int r = 0;
+            for (; r + 1 < R; r += 2) pairC(vs[r * NB], vs[(r + 1) * NB], wgt(r), wgt(r + 1));
+            if (r < R) singleC(vs[r * NB], wgt(r));
           }
           cl += sl;
-          cr = fmaf(vs[(size_t)R * PS], sr, cr);
+          cr = fmaf(vs[R * NB], sr, cr);
         }
       }
       __syncthreads();                                      // chunk j is free (and `red` of pass B is consumed)
@@ -414,56 +479,58 @@ __global__ void __launch_bounds__(CT, 1) k_cols_v1(ColsArgs p) {
   cp_wait_dyn(0);
 }
 
-template <int KMAX>
+template <int KMAX, int RT>
 int32_t launch_cols(const ColsArgs& a, size_t smem, int grid, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(k_cols_v1<KMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(k_cols_v1<KMAX, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return fail(GVN_E_CUDA, "k_cols_v1 smem attr (%zu B): %s", smem, cudaGetErrorString(e));
-  k_cols_v1<KMAX><<<grid, CT, smem, st>>>(a);
+  k_cols_v1<KMAX, RT><<<grid, CT, smem, st>>>(a);
   return check_launch("k_cols_v1");
 }
 
 inline int kmax_of(int K) { return (K + 3) / 4 * 4; }
 inline int ks_of(int K) { int ks = kmax_of(K); return (ks % 16 == 0) ? ks + 4 : ks; }
+inline int rs_of(int R) { return (R + 1) | 1; }
+
+template <int KMAX>
+int32_t launch_v1_k(const gvn_batch* b, int R, const ColsArgs& a, size_t smem, int grid, cudaStream_t st) {
+  dim3 gw((b->F + CT / 32 - 1) / (CT / 32), b->B);
+  if (R == 10)
+    k_w_v1<KMAX, 10><<<gw, CT, 0, st>>>(b->F, b->K, b->NP, R, b->frame_off, b->n_frames, b->X2, b->Vs, b->Vs_w, b->Vb, b->g, b->H, b->W, b->Wun);
+  else
+    k_w_v1<KMAX, 0><<<gw, CT, 0, st>>>(b->F, b->K, b->NP, R, b->frame_off, b->n_frames, b->X2, b->Vs, b->Vs_w, b->Vb, b->g, b->H, b->W, b->Wun);
+  int32_t rc = check_launch("k_w_v1");
+  if (rc) return rc;
+  return R == 10 ? launch_cols<KMAX, 10>(a, smem, grid, st) : launch_cols<KMAX, 0>(a, smem, grid, st);
+}
 
 }  // namespace
 
 // true when variant 1 can run this shape (the tile block must fit in shared memory)
 bool mstep_v1_supported(const gvn_batch* b, int R) {
   if (b->K > 16) return false;
-  const size_t bytes = cols_smem_floats(b->F, ks_of(b->K), R, kmax_of(b->K)) * 4;
+  const size_t bytes = cols_smem_floats(b->F, ks_of(b->K), R, rs_of(R), kmax_of(b->K)) * 4;
   return bytes <= 227 * 1024;
 }
 
 int32_t launch_mstep_v1(const gvn_batch* b, int R, float* cost_part, cudaStream_t st) {
   const int KMAX = kmax_of(b->K);
-  dim3 gw((b->F + CT / 32 - 1) / (CT / 32), b->B);
-#define GVN_W(KM) k_w_v1<KM><<<gw, CT, 0, st>>>(b->F, b->K, b->NP, R, b->frame_off, b->n_frames, b->X2, b->Vs, b->Vb, b->g, b->H, b->W, b->Wun)
-  switch (KMAX) {
-    case 4: GVN_W(4); break;
-    case 8: GVN_W(8); break;
-    case 12: GVN_W(12); break;
-    default: GVN_W(16); break;
-  }
-#undef GVN_W
-  int32_t rc = check_launch("k_w_v1");
-  if (rc) return rc;
   ColsArgs a;
-  a.F = b->F; a.K = b->K; a.KS = ks_of(b->K); a.NP = b->NP; a.R = R; a.B = b->B;
+  a.F = b->F; a.K = b->K; a.KS = ks_of(b->K); a.NP = b->NP; a.R = R; a.RS = rs_of(R); a.B = b->B;
   a.ntiles = b->NP / NB;
   const int NI = (b->F + 31) / 32;
   a.nchunk = NI < MAXCH ? NI : MAXCH;
-  a.frame_utt = b->frame_utt; a.frame_off = b->frame_off; a.X2 = b->X2; a.Vs = b->Vs;
+  a.frame_utt = b->frame_utt; a.frame_off = b->frame_off; a.X2 = b->X2; a.Vs = b->Vs; a.Vs_w = b->Vs_w;
   a.Vb = b->Vb; a.g = b->g; a.H = b->H; a.Wun = b->Wun; a.W = b->W; a.cost_part = cost_part;
-  const size_t smem = cols_smem_floats(b->F, a.KS, R, KMAX) * 4;
+  const size_t smem = cols_smem_floats(b->F, a.KS, R, a.RS, KMAX) * 4;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  int grid = a.ntiles < sms ? a.ntiles : sms;
+  const int grid = a.ntiles < sms ? a.ntiles : sms;
   switch (KMAX) {
-    case 4: return launch_cols<4>(a, smem, grid, st);
-    case 8: return launch_cols<8>(a, smem, grid, st);
-    case 12: return launch_cols<12>(a, smem, grid, st);
-    default: return launch_cols<16>(a, smem, grid, st);
+    case 4: return launch_v1_k<4>(b, R, a, smem, grid, st);
+    case 8: return launch_v1_k<8>(b, R, a, smem, grid, st);
+    case 12: return launch_v1_k<12>(b, R, a, smem, grid, st);
+    default: return launch_v1_k<16>(b, R, a, smem, grid, st);
   }
 }
 

@@ -131,7 +131,9 @@ class Batch:
         self.g = torch.ones(NP, **f32)
         self.Vb = torch.ones(F, NP, **f32)
         self.Z = torch.zeros(L, NP, **f32)
-        self.Vs = torch.empty(R_cap, F, NP, **f32)
+        self.Vs = torch.zeros(R_cap, F, NP, **f32)          # slot form, see include/gvn.h
+        self.Vs_w = torch.zeros(R_cap, NP, **f32)
+        self.XV = torch.empty(F, NP, dtype=torch.int32, device=device)
         self.yproj = torch.zeros(GVN_HIDDEN, NP, **f32)
         self.y = None
         self._struct = None
@@ -139,7 +141,7 @@ class Batch:
     def struct(self):
         s = GvnBatch()
         s.B, s.F, s.K, s.L, s.NP, s.R_cap = self.B, self.F, self.K, self.L, self.NP, self.R_cap
-        for name in ("frame_off", "n_frames", "frame_utt", "X2", "Xc", "W", "Wun", "H", "g", "Vb", "Z", "Vs", "yproj"):
+        for name in ("frame_off", "n_frames", "frame_utt", "X2", "Xc", "W", "Wun", "H", "g", "Vb", "Z", "Vs", "yproj", "Vs_w", "XV"):
             t = getattr(self, name)
             setattr(s, name, 0 if t is None else t.data_ptr())
         self._struct = s
@@ -157,6 +159,15 @@ class Batch:
 
     def gather_cols(self, src, b):
         return src[..., self.cols(b)]
+
+    def expand_samples(self, R, b=None):
+        """The reference's Vs (R,F,N) (mcem.py:307) from the slot form: sample r is the last slot
+        <= r with a non-zero multiplicity.  For tests and the `Vs` attribute of the drop-in classes."""
+        w = self.Vs_w[:R]
+        idx = torch.arange(R, device=w.device).unsqueeze(1) * (w > 0)
+        src = torch.cummax(idx, dim=0).values                              # (R, NP)
+        out = torch.gather(self.Vs[:R], 0, src.unsqueeze(1).expand(R, self.F, self.NP))
+        return out if b is None else out[..., self.cols(b)]
 
 
 # --------------------------------------------------------------------------------------

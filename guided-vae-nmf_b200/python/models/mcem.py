@@ -30,7 +30,7 @@ class EM:
 
     def __init__(self, niter=100):
         self.niter = niter
-        self.Vs = None
+        self._R = None
         self.precision = "fp32"        # "fp32" | "f16x3" | "f16"  (decoder arithmetic)
         self.mstep_variant = 1
         self.seed = None               # Philox seed; None -> derived from torch's seed
@@ -47,6 +47,11 @@ class EM:
     Z = property(lambda self: self._cols(self._batch.Z))
     Vb = property(lambda self: self._cols(self._batch.Vb))
     X_abs_2 = property(lambda self: self._cols(self._batch.X2))
+
+    @property
+    def Vs(self):
+        """(R,F,N) speech variance of the kept samples (mcem.py:307), expanded from the slot form."""
+        return None if self._R is None or self._batch is None else self._batch.expand_samples(self._R, 0)
 
     @property
     def Vs_scaled(self):
@@ -92,7 +97,7 @@ class EM:
             _E.set_labels(b, dec, yd)
             _E.encode_init(b, vae)
         self.X_abs_2_t = self.X_abs_2
-        self.Vs = None
+        self._R = None
         self._iter = 0
         self._scratch = None
         self._chain = 0
@@ -123,7 +128,6 @@ class EM:
             out = _E.estep(b, self._dec, burnin, R, self.var_RW, self.precision, self._seed, self._chain,
                            eps, u, forced, trace)
         self._chain += 1
-        self.Vs = b.Vs[:R][..., b.cols(0)]
         self._R = R
         if trace:
             acc, dec_, cnt, zs = out

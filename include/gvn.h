@@ -30,7 +30,15 @@
  *    Vb   [F][NP]  f32   noise variance W@H        (mcem.py:82; NOT refreshed after the
  *                                                   normalisation, as in mcem.py:124-133)
  *    Z    [L][NP]  f32   current latent state      (mcem.py:215, 319)
- *    Vs   [R][F][NP] f32 speech variance of the R kept samples (mcem.py:307)
+ *    Vs   [R][F][NP] f32 speech variance of the kept samples (mcem.py:307), slot form: slot r
+ *                        holds the decoder output of the PROPOSAL of kept step r (slot 0: the state
+ *                        after the burn-in) and
+ *    Vs_w [R][NP]    f32 its multiplicity: 0 when that proposal was rejected, 1 + (number of
+ *                        following rejected steps) otherwise.  A Metropolis-Hastings reject repeats
+ *                        the previous sample (mcem.py:280-289), so sum_r phi(Vs_r) of the reference
+ *                        equals sum_slot Vs_w[slot] * phi(Vs[slot]); nothing is ever copied.
+ *                        sum_slot Vs_w[slot][n] == R for every frame.
+ *    XV   [F][NP]    u32 scratch of the tensor-core chain: bf16(X2) << 16 | bf16(Vb)
  *    yproj[HID][NP] f32  b1 + W1[:, L:] @ y  -- the label part of the decoder's first layer,
  *                        constant per utterance (mcem.py:242 concatenates y every step)
  */
@@ -82,6 +90,8 @@ typedef struct gvn_batch {
   float* Z;
   float* Vs;
   const float* yproj;
+  float* Vs_w;
+  uint32_t* XV;                   /* may be NULL when only GVN_PREC_FP32 is used            */
 } gvn_batch;
 
 /* random input of one Metropolis-Hastings chain (mcem.py:257 randn(L,N), :271 rand(N)).
@@ -121,7 +131,8 @@ int32_t gvn_label_projection(const void* packed, const float* y, int32_t L, int3
 
 /* One MH chain for every frame of the batch: replaces sample_posterior + compute_Vs
  * (mcem.py:218-307 / :371-454).  n_steps = burnin + R.  On return Z holds the last kept
- * sample (mcem.py:319) and Vs[0..R) the speech variance of the kept samples. */
+ * sample (mcem.py:319) and Vs[0..R) / Vs_w[0..R) the speech variance of the kept samples in
+ * slot form (see the layout comment above). */
 int32_t gvn_estep(const gvn_batch* batch /*HOST*/, const void* packed, int32_t burnin, int32_t R,
                   float var_RW, const gvn_noise* noise /*HOST*/, const gvn_trace* trace /*HOST or NULL*/,
                   int32_t precision, void* stream);

@@ -18,6 +18,10 @@ def _random_batch(n_frames, F, K, L, R, seed):
     b.g.copy_(torch.rand(b.NP, generator=g, device="cuda") + 0.5)
     b.H.copy_(torch.rand(K, b.NP, generator=g, device="cuda") + 1e-3)
     b.W.copy_(torch.rand(b.B, F, K, generator=g, device="cuda") + 1e-3)
+    # slot multiplicities (include/gvn.h): slot 0 always live, some slots dead (rejected proposals)
+    w = torch.randint(0, 3, (R, b.NP), generator=g, device="cuda").float()
+    w[0] += 1
+    b.Vs_w.copy_(w)
     # poison the padding columns of Vs: they must never be read into a result
     pad = b.frame_utt < 0
     b.Vs[:, :, pad] = float("nan")
