@@ -181,8 +181,8 @@ __global__ void __launch_bounds__(NT, 2) k_estep_simt(EstepArgs p) {
                 cs[i] += (double)(logf(vx) + x2v[i] / vx);
               }
             }
-            if (vs_out != nullptr)
-              *reinterpret_cast<float4*>(vs_out + off) = make_float4(vs[0], vs[1], vs[2], vs[3]);
+            if (vs_out != nullptr)    // column-tile order; nb is a multiple of 4, so the four frames stay adjacent
+              *reinterpret_cast<float4*>(vs_out + tile_off(f, nb, F)) = make_float4(vs[0], vs[1], vs[2], vs[3]);
           }
         }
       }

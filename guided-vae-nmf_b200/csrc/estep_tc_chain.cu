@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_estep_tc(const __grid_constant_
       hidden(std::true_type{});
       hidden(std::false_type{});
       double dl = 0.0, dr = 0.0;
-      float* vo = STORE ? vs_out + (size_t)(16 * half) * NP + n : nullptr;
+      float* vo = STORE ? vs_out + tile_off(16 * half, n, F) : nullptr;   // column-tile order: bin stride = 8 floats
 #pragma unroll 1
       for (int c = 0; c < NCH; ++c) {
         const int buf = c & 1, ncol = min(128, FN - c * 128);
@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_estep_tc(const __grid_constant_
                 const float qn = fmaf(__uint_as_float(w0 & 0xffff0000u), b, __uint_as_float(w1 & 0xffff0000u) * a);
                 sr = fmaf(qn, rcp_approx(pr), sr);
               }
-              if (STORE && valid) { vo[(size_t)(2 * j) * NP] = v0; vo[(size_t)(2 * j + 1) * NP] = v1; }
+              if (STORE && valid) { vo[(2 * j) * 8] = v0; vo[(2 * j + 1) * 8] = v1; }
             }
           } else {                                         // ragged tail of the spectrum (F = 513: one bin)
             const int nv = F - f0;
@@ -346,10 +346,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_estep_tc(const __grid_constant_
                 sl += lg2_approx(a);
                 sr = fmaf(__uint_as_float(w0 & 0xffff0000u), rcp_approx(a), sr);
               }
-              if (STORE && valid) vo[(size_t)j * NP] = v0;
+              if (STORE && valid) vo[j * 8] = v0;
             }
           }
-          if (STORE) vo += (size_t)SROWS * NP;
+          if (STORE) vo += SROWS * 8;
           if (ENERGY) {
             dl += (double)sl;
             dr += (double)sr;

@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(256) k_mstep_w(int F, int K, int NP, int R, co
     const int gn = n_begin + n;
     const float gg = g[gn], vb = Vb[row + gn], x2 = X2[row + gn];
     float s1 = 0.f, s2 = 0.f;
-    const float* vsp = Vs + row + gn;
+    const float* vsp = Vs + tile_off(f, gn, F);
 #pragma unroll 5
     for (int r = 0; r < R; ++r) {
       float vx = fmaf(gg, vsp[(size_t)r * slab], vb);
@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(256) k_mstep_cols(int F, int K, int NP, int R,
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll 5
     for (int r = 0; r < R; ++r) {
-      float inv = 1.0f / fmaf(gg, Vs[o + (size_t)r * slab], vb), wi = Vs_w[(size_t)r * NP + gn] * inv;
+      float inv = 1.0f / fmaf(gg, Vs[tile_off(f, gn, F) + (size_t)r * slab], vb), wi = Vs_w[(size_t)r * NP + gn] * inv;
       s1 += wi;
       s2 = fmaf(wi, inv, s2);
     }
@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(256) k_mstep_cols(int F, int K, int NP, int R,
     float t2 = 0.f, t1 = 0.f;
 #pragma unroll 5
     for (int r = 0; r < R; ++r) {
-      float vs = Vs[o + (size_t)r * slab];
+      float vs = Vs[tile_off(f, gn, F) + (size_t)r * slab];
       float inv = 1.0f / fmaf(gg, vs, vb), wv = Vs_w[(size_t)r * NP + gn] * vs;
       t1 = fmaf(wv, inv, t1);
       t2 = fmaf(wv * inv, inv, t2);
@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(256) k_mstep_cols(int F, int K, int NP, int R,
       float c = 0.f;
 #pragma unroll 5
       for (int r = 0; r < R; ++r) {
-        float vx = fmaf(gnew, Vs[o + (size_t)r * slab], vb);
+        float vx = fmaf(gnew, Vs[tile_off(f, gn, F) + (size_t)r * slab], vb);
         c = fmaf(Vs_w[(size_t)r * NP + gn], logf(vx) + x2 / vx, c);
       }
       cs += c;
@@ -251,12 +251,12 @@ __global__ void __launch_bounds__(256) k_wiener(int F, int NP, int R, const int3
                                                 float* __restrict__ WFs, float* __restrict__ WFn) {
   const size_t total = (size_t)F * NP, slab = total;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int gn = (int)(i % NP);
+    const int gn = (int)(i % NP), f = (int)(i / NP);
     float ws = 0.f, wn = 0.f;
     if (frame_utt[gn] >= 0) {
       const float gg = g[gn], vb = Vb[i];
       for (int r = 0; r < R; ++r) {
-        float sc = gg * Vs[i + (size_t)r * slab], w = Vs_w[(size_t)r * NP + gn];
+        float sc = gg * Vs[tile_off(f, gn, F) + (size_t)r * slab], w = Vs_w[(size_t)r * NP + gn];
         float vx = sc + vb;
         ws = fmaf(w, sc / vx, ws);
         wn = fmaf(w, vb / vx, wn);
@@ -280,7 +280,7 @@ __global__ void k_init_nmf_w(size_t n, const float* __restrict__ rnd, float eps,
 __global__ void k_init_nmf_cols(int F, int K, int NP, const int32_t* __restrict__ frame_utt,
                                 const float* __restrict__ rndH, float eps, const float* __restrict__ W,
                                 float* __restrict__ H, float* __restrict__ g, float* __restrict__ Vb,
-                                float* __restrict__ X2, float2* __restrict__ Xc) {
+                                float* __restrict__ X2, float2* __restrict__ Xc, float* __restrict__ X2t) {
   const int gn = blockIdx.x * blockDim.x + threadIdx.x;
   if (gn >= NP) return;
   const int b = frame_utt[gn];
@@ -290,6 +290,7 @@ __global__ void k_init_nmf_cols(int F, int K, int NP, const int32_t* __restrict_
     for (int f = 0; f < F; ++f) {
       Vb[(size_t)f * NP + gn] = 1.f;
       X2[(size_t)f * NP + gn] = 1.f;
+      if (X2t != nullptr) X2t[tile_off(f, gn, F)] = 1.f;
       if (Xc != nullptr) Xc[(size_t)f * NP + gn] = make_float2(0.f, 0.f);
     }
     return;
@@ -301,6 +302,7 @@ __global__ void k_init_nmf_cols(int F, int K, int NP, const int32_t* __restrict_
     float vb = 0.f;
     for (int k = 0; k < K; ++k) vb = fmaf(w[(size_t)f * K + k], h[k], vb);
     Vb[(size_t)f * NP + gn] = vb;
+    if (X2t != nullptr) X2t[tile_off(f, gn, F)] = X2[(size_t)f * NP + gn];   // column-tile copy for the M-step
   }
 }
 
@@ -361,7 +363,7 @@ int32_t launch_init_nmf(const gvn_batch* b, const float* rand_W, const float* ra
   int32_t rc = check_launch("k_init_nmf_w");
   if (rc) return rc;
   k_init_nmf_cols<<<(b->NP + 127) / 128, 128, 0, st>>>(b->F, b->K, b->NP, b->frame_utt, rand_H, eps, b->W, b->H, b->g,
-                                                       b->Vb, b->X2, reinterpret_cast<float2*>(b->Xc));
+                                                       b->Vb, b->X2, reinterpret_cast<float2*>(b->Xc), b->X2t);
   return check_launch("k_init_nmf_cols");
 }
 

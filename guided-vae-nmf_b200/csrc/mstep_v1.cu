@@ -69,130 +69,162 @@ __device__ __forceinline__ void single_acc(float g, float vb, float va, float wa
   s2 = fmaf(ta, ia, s2);
 }
 
+// ---- bulk async copies (TMA engine, no tensor map) + mbarrier -------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(s_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  for (uint32_t spins = 0; !ok; ++spins) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(s_u32(bar)), "r"(parity) : "memory");
+    if (spins > (1u << 26)) __trap();       // a protocol bug must surface as an error, not a hang
+  }
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s_u32(dst)),
+               "l"(src), "r"(bytes), "r"(s_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
 // ------------------------------------------------------------------ W update (mcem.py:105-110)
+// One CTA per (utterance, block of 64 frequency rows); thread = (row, column n of an 8-frame
+// tile).  The [rows][8] blocks of the R sample slots and of X2 (column-tile order: contiguous
+// rows*32 bytes each) stream through a ring of WS stages filled by bulk async copies, so the
+// bytes in flight live in shared memory, not in registers.  Vb of the reference is W @ H here
+// (the stored Vb is the same product before the normalisation, mcem.py:124-133).
+constexpr int WROWS = 64;             // frequency rows per CTA
+constexpr int WT = WROWS * NB;        // 512 threads
+constexpr int WS = 4;                 // ring stages (two CTAs per SM: 8 stages of ~23 KB in flight)
+
+// floats of one ring stage: (R+1) planes of [WROWS][NB] + column data (H rows, g, multiplicities)
+__host__ __device__ inline int w_stage_floats(int K, int R) { return ((R + 1) * WROWS * NB + (K + 1 + R) * NB + 31) / 32 * 32; }
+
 template <int KMAX, int RT>
-__global__ void __launch_bounds__(CT) k_w_v1(int F, int K, int NP, int R_rt, const int32_t* __restrict__ frame_off,
-                                             const int32_t* __restrict__ n_frames, const float* __restrict__ X2,
-                                             const float* __restrict__ Vs, const float* __restrict__ Vs_w,
-                                             const float* __restrict__ Vb, const float* __restrict__ g,
-                                             const float* __restrict__ H, const float* __restrict__ W,
-                                             float* __restrict__ Wun) {
+__global__ void __launch_bounds__(WT, 2) k_w_v2(int F, int K, int NP, int R_rt, const int32_t* __restrict__ frame_off,
+                                                const int32_t* __restrict__ n_frames, const float* __restrict__ X2t,
+                                                const float* __restrict__ Vs, const float* __restrict__ Vs_w,
+                                                const float* __restrict__ g, const float* __restrict__ H,
+                                                const float* __restrict__ W, float* __restrict__ Wun) {
+  extern __shared__ __align__(128) float smw[];             // [WS][stage]
+  __shared__ __align__(8) uint64_t full[WS];
   const int R = RT > 0 ? RT : R_rt;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.y, f = blockIdx.x * (CT / 32) + warp;
-  if (f >= F) return;
+  const int tid = threadIdx.x, n = tid & (NB - 1), rl = tid >> 3;
+  const int b = blockIdx.y, f0 = blockIdx.x * WROWS, f = f0 + rl;
+  const int rows = min(WROWS, F - f0);
+  const bool rowok = rl < rows;
   const int n_begin = frame_off[b], N = n_frames[b];
-  const int NPAD = (N + GVN_FRAME_ALIGN - 1) / GVN_FRAME_ALIGN * GVN_FRAME_ALIGN;
-  float num[KMAX], den[KMAX];
-#pragma unroll
-  for (int k = 0; k < KMAX; ++k) num[k] = den[k] = 0.f;
-  const size_t row = (size_t)f * NP, slab = (size_t)F * NP;
-  for (int n4 = lane * 4; n4 < NPAD; n4 += 128) {
-    const size_t o = row + n_begin + n4;
-    const float* vsp = Vs + o;
-    const float* wp = Vs_w + n_begin + n4;
-    const float4 vb = ldg_stream4(Vb + o), x2 = ldg_stream4(X2 + o);
-    const float4 gg = __ldg(reinterpret_cast<const float4*>(g + n_begin + n4));
-    float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
-    if (RT > 0) {
-      float4 v[RT > 0 ? RT : 1];
-#pragma unroll
-      for (int r = 0; r < RT; ++r) v[r] = ldg_stream4(vsp + (size_t)r * slab);     // all slots in flight
-#pragma unroll
-      for (int r = 0; r + 1 < RT; r += 2) {
-        const float4 wa = __ldg(reinterpret_cast<const float4*>(wp + (size_t)r * NP));
-        const float4 wc = __ldg(reinterpret_cast<const float4*>(wp + (size_t)(r + 1) * NP));
-        pair_acc(gg.x, vb.x, v[r].x, v[r + 1].x, wa.x, wc.x, s1.x, s2.x);
-        pair_acc(gg.y, vb.y, v[r].y, v[r + 1].y, wa.y, wc.y, s1.y, s2.y);
-        pair_acc(gg.z, vb.z, v[r].z, v[r + 1].z, wa.z, wc.z, s1.z, s2.z);
-        pair_acc(gg.w, vb.w, v[r].w, v[r + 1].w, wa.w, wc.w, s1.w, s2.w);
-      }
-      if (RT & 1) {
-        const float4 wa = __ldg(reinterpret_cast<const float4*>(wp + (size_t)(RT - 1) * NP));
-        single_acc(gg.x, vb.x, v[RT - 1].x, wa.x, s1.x, s2.x);
-        single_acc(gg.y, vb.y, v[RT - 1].y, wa.y, s1.y, s2.y);
-        single_acc(gg.z, vb.z, v[RT - 1].z, wa.z, s1.z, s2.z);
-        single_acc(gg.w, vb.w, v[RT - 1].w, wa.w, s1.w, s2.w);
-      }
-    } else {
-      int r = 0;
-#pragma unroll 2
-      for (; r + 1 < R; r += 2) {
-        const float4 va = ldg_stream4(vsp + (size_t)r * slab), vc = ldg_stream4(vsp + (size_t)(r + 1) * slab);
-        const float4 wa = __ldg(reinterpret_cast<const float4*>(wp + (size_t)r * NP));
-        const float4 wc = __ldg(reinterpret_cast<const float4*>(wp + (size_t)(r + 1) * NP));
-        pair_acc(gg.x, vb.x, va.x, vc.x, wa.x, wc.x, s1.x, s2.x);
-        pair_acc(gg.y, vb.y, va.y, vc.y, wa.y, wc.y, s1.y, s2.y);
-        pair_acc(gg.z, vb.z, va.z, vc.z, wa.z, wc.z, s1.z, s2.z);
-        pair_acc(gg.w, vb.w, va.w, vc.w, wa.w, wc.w, s1.w, s2.w);
-      }
-      if (r < R) {
-        const float4 va = ldg_stream4(vsp + (size_t)r * slab);
-        const float4 wa = __ldg(reinterpret_cast<const float4*>(wp + (size_t)r * NP));
-        single_acc(gg.x, vb.x, va.x, wa.x, s1.x, s2.x);
-        single_acc(gg.y, vb.y, va.y, wa.y, s1.y, s2.y);
-        single_acc(gg.z, vb.z, va.z, wa.z, s1.z, s2.z);
-        single_acc(gg.w, vb.w, va.w, wa.w, s1.w, s2.w);
-      }
-    }
-    float4 a = make_float4(x2.x * s2.x, x2.y * s2.y, x2.z * s2.z, x2.w * s2.w);
-    // frames beyond the utterance (padding up to the 32-frame boundary) contribute nothing
-    if (n4 + 0 >= N) { a.x = 0.f; s1.x = 0.f; }
-    if (n4 + 1 >= N) { a.y = 0.f; s1.y = 0.f; }
-    if (n4 + 2 >= N) { a.z = 0.f; s1.z = 0.f; }
-    if (n4 + 3 >= N) { a.w = 0.f; s1.w = 0.f; }
-#pragma unroll
-    for (int k = 0; k < KMAX; ++k) {
-      if (k < K) {
-        const float4 h = __ldg(reinterpret_cast<const float4*>(H + (size_t)k * NP + n_begin + n4));
-        num[k] = fmaf(a.x, h.x, fmaf(a.y, h.y, fmaf(a.z, h.z, fmaf(a.w, h.w, num[k]))));
-        den[k] = fmaf(s1.x, h.x, fmaf(s1.y, h.y, fmaf(s1.z, h.z, fmaf(s1.w, h.w, den[k]))));
-      }
-    }
+  const int ntile = (N + NB - 1) / NB, t0 = n_begin / NB, T8 = NP / NB;
+  constexpr int PSt = WROWS * NB;                           // plane stride inside a stage (floats)
+  const int MO = (R + 1) * PSt;                             // offset of the column data inside a stage
+  const int SSt = w_stage_floats(K, R);
+  const uint32_t blk = (uint32_t)rows * NB * 4;             // bytes of one plane block
+  const int ncopy = (R + 1) + (K + 1 + R);
+
+  if (tid == 0) {
+    for (int s = 0; s < WS; ++s) mbar_init(full + s, 1);
+    fence_mbar_init();
   }
+  __syncthreads();
+  // warp 0: lane i issues copy i of tile ti into stage ti % WS (plane blocks, then 32-byte column rows)
+  auto issue = [&](int ti) {
+    const int s = ti % WS, lane = tid;
+    float* dst = smw + (size_t)s * SSt;
+    const size_t col = (size_t)n_begin + (size_t)ti * NB;
+    if (lane == 0) mbar_expect_tx(full + s, blk * (R + 1) + (uint32_t)(K + 1 + R) * NB * 4);
+    __syncwarp();
+    for (int c = lane; c < ncopy; c += 32) {
+      if (c < R) bulk_g2s(dst + c * PSt, Vs + (((size_t)c * T8 + t0 + ti) * F + f0) * NB, blk, full + s);
+      else if (c == R) bulk_g2s(dst + R * PSt, X2t + ((size_t)(t0 + ti) * F + f0) * NB, blk, full + s);
+      else {
+        const int m = c - R - 1;                            // 0..K-1: H rows, K: g, K+1..: multiplicities
+        const float* src = m < K ? H + (size_t)m * NP + col : (m == K ? g + col : Vs_w + (size_t)(m - K - 1) * NP + col);
+        bulk_g2s(dst + MO + m * NB, src, NB * 4, full + s);
+      }
+    }
+  };
+  if (tid < 32) for (int ti = 0; ti < WS && ti < ntile; ++ti) issue(ti);
+
+  float w[KMAX], num[KMAX], den[KMAX];
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) { w[k] = (k < K && rowok) ? W[((size_t)b * F + f) * K + k] : 0.f; num[k] = den[k] = 0.f; }
+
+  for (int ti = 0; ti < ntile; ++ti) {
+    const int s = ti % WS;
+    mbar_wait(full + s, (ti / WS) & 1);
+    if (rowok) {
+      const float* st = smw + (size_t)s * SSt;
+      const float* vs = st + rl * NB + n;
+      const float* mt = st + MO + n;                        // column data of frame n
+      float vb = 0.f;
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) if (k < K) vb = fmaf(w[k], mt[k * NB], vb);
+      const float gg = mt[K * NB];
+      const float* wt = mt + (K + 1) * NB;
+      float s1 = 0.f, s2 = 0.f;
+      if (RT > 0) {
+#pragma unroll
+        for (int r = 0; r + 1 < RT; r += 2) pair_acc(gg, vb, vs[r * PSt], vs[(r + 1) * PSt], wt[r * NB], wt[(r + 1) * NB], s1, s2);
+        if (RT & 1) single_acc(gg, vb, vs[(RT - 1) * PSt], wt[(RT - 1) * NB], s1, s2);
+      } else {
+        int r = 0;
+        for (; r + 1 < R; r += 2) pair_acc(gg, vb, vs[r * PSt], vs[(r + 1) * PSt], wt[r * NB], wt[(r + 1) * NB], s1, s2);
+        if (r < R) single_acc(gg, vb, vs[r * PSt], wt[r * NB], s1, s2);
+      }
+      float a = vs[R * PSt] * s2;
+      if (ti * NB + n >= N) { a = 0.f; s1 = 0.f; }          // padding frames of the last tile contribute nothing
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) if (k < K) { const float h = mt[k * NB]; num[k] = fmaf(a, h, num[k]); den[k] = fmaf(s1, h, den[k]); }
+    }
+    __syncthreads();                                        // stage s is free
+    if (tid < 32 && ti + WS < ntile) { fence_proxy_async(); issue(ti + WS); }
+  }
+  // reduce over the 8 columns of the tile (adjacent lanes), lane n == 0 writes the row
 #pragma unroll
   for (int k = 0; k < KMAX; ++k) {
-    if (k < K) {
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        num[k] += __shfl_xor_sync(0xffffffffu, num[k], o);
-        den[k] += __shfl_xor_sync(0xffffffffu, den[k], o);
-      }
+    for (int o = 4; o > 0; o >>= 1) {
+      num[k] += __shfl_xor_sync(0xffffffffu, num[k], o);
+      den[k] += __shfl_xor_sync(0xffffffffu, den[k], o);
     }
   }
+  if (n == 0 && rowok) {
 #pragma unroll
-  for (int k = 0; k < KMAX; ++k) {
-    if (k < K && lane == k) {
-      const size_t o = ((size_t)b * F + f) * K + k;
-      Wun[o] = W[o] * sqrtf(num[k] / den[k]);
-    }
+    for (int k = 0; k < KMAX; ++k)
+      if (k < K) Wun[((size_t)b * F + f) * K + k] = w[k] * sqrtf(num[k] / den[k]);
   }
 }
 
 // ------------------------------------------- column sweep: H, Vb, normalisation, g, cost
 struct ColsArgs {
-  int F, K, KS, NP, R, RS, B, ntiles, nchunk;
+  int F, K, KS, NP, R, B, ntiles, nchunk;
   const int32_t* frame_utt; const int32_t* frame_off;
-  const float* X2; const float* Vs; const float* Vs_w;
-  float* Vb; float* g; float* H; const float* Wun; float* W; float* cost_part;
+  const float* X2t; const float* Vs; const float* Vs_w;
+  float* Vb; float* g; float* H; const float* Wun; float* W; float* cost_part; uint32_t* XV;
 };
 
-// shared memory (floats): data[F][RS][NB] (slot r of bin f at [f][r], X2 at [f][R]) | W_s[F][KS] |
-// red[8][2*KMAX][NB] | red2[2*KMAX][NB] | Hn_s[KMAX][NB] | meta[(KMAX+2+R)][NB] | wts_s[R][NB] | cn_s[KMAX] | misc[32]
-__host__ __device__ inline size_t cols_smem_floats(int F, int KS, int R, int RS, int KMAX) {
-  return (size_t)F * RS * NB + (size_t)F * KS + (size_t)8 * 2 * KMAX * NB + (size_t)2 * KMAX * NB + (size_t)KMAX * NB +
-         (size_t)(KMAX + 2 + R) * NB + (size_t)R * NB + KMAX + 32;
+// shared memory (floats): data[(R+1)][F][NB] (plane R = X2) | W_s[F][KS] | red[8][2*KMAX][NB] |
+// red2[2*KMAX][NB] | Hn_s[KMAX][NB] | meta[(KMAX+2+R)][NB] | wts_s[R][NB] | cn_s[KMAX] | misc[32] | bars[MAXCH]
+__host__ __device__ inline size_t cols_smem_floats(int F, int KS, int R, int KMAX) {
+  return (size_t)(R + 1) * F * NB + (size_t)F * KS + (size_t)8 * 2 * KMAX * NB + (size_t)2 * KMAX * NB + (size_t)KMAX * NB +
+         (size_t)(KMAX + 2 + R) * NB + (size_t)R * NB + KMAX + 32 + 2 * MAXCH + 4;
 }
 
 template <int KMAX, int RT>
 __global__ void __launch_bounds__(CT, 1) k_cols_v1(ColsArgs p) {
-  extern __shared__ __align__(16) float sm[];
+  extern __shared__ __align__(128) float sm[];
   const int F = p.F, K = p.K, KS = p.KS, NP = p.NP;
   const int R = RT > 0 ? RT : p.R;
-  const int RS = RT > 0 ? ((RT + 1) | 1) : p.RS;            // row stride in 8-float groups (odd: conflict-free)
-  const int FS = RS * NB;                                   // floats per frequency row
+  const int PS = F * NB;                                    // plane stride (floats); a plane is one bulk-contiguous block
   float* data = sm;
-  float* W_s = data + (size_t)F * FS;
+  float* W_s = data + (size_t)(R + 1) * PS;
   float* red = W_s + (size_t)F * KS;
   float* red2 = red + 8 * 2 * KMAX * NB;
   float* Hn_s = red2 + 2 * KMAX * NB;
@@ -200,10 +232,11 @@ __global__ void __launch_bounds__(CT, 1) k_cols_v1(ColsArgs p) {
   float* wts_s = meta + (KMAX + 2 + R) * NB;                // [R][NB] multiplicities of the current tile
   float* cn_s = wts_s + R * NB;
   float* misc = cn_s + KMAX;
+  uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(misc + 32) + 7) & ~(uintptr_t)7);   // [MAXCH]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n = tid & (NB - 1), fl = tid >> 3;              // column of the tile, frequency lane (0..31)
-  const int NI = (F + 31) / 32, NCH = p.nchunk;
+  const int NI = (F + 31) / 32, NCH = p.nchunk, T8 = NP / NB;
 
   // contiguous tile range of this CTA, walked from the END of the batch: the W sweep that ran
   // just before leaves the tail of Vs in L2
@@ -213,46 +246,56 @@ __global__ void __launch_bounds__(CT, 1) k_cols_v1(ColsArgs p) {
   if (t_lo < 0) t_lo = 0;
   if (t_hi <= 0) return;
 
+  if (tid == 0) {
+    for (int j = 0; j < NCH; ++j) mbar_init(bars + j, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  // warp 0: rows [r0, r1) of every plane of tile t, one bulk copy per plane (lane = plane)
   auto issue_chunk = [&](int t, int j) {
     const int i0 = j * NI / NCH, i1 = (j + 1) * NI / NCH;
     const int r0 = i0 * 32, r1 = min(i1 * 32, F);
-    const int rows2 = (r1 - r0) * 2;
-    const size_t col = (size_t)t * NB;
-    const int total = rows2 * (R + 1);
-    const bool pow2 = rows2 == 128;
-    for (int q = tid; q < total; q += CT) {
-      const int plane = pow2 ? (q >> 7) : q / rows2;
-      const int rem = pow2 ? (q & 127) : q - plane * rows2;
-      const int rowi = r0 + (rem >> 1), half = rem & 1;
-      const float* src = (plane < R ? p.Vs + ((size_t)plane * F + rowi) * NP : p.X2 + (size_t)rowi * NP) + col + 4 * half;
-      cp16(data + (size_t)rowi * FS + plane * NB + 4 * half, src);
+    const uint32_t bytes = (uint32_t)(r1 - r0) * NB * 4;
+    if (lane == 0) mbar_expect_tx(bars + j, bytes * (R + 1));
+    __syncwarp();
+    for (int pl = lane; pl <= R; pl += 32) {
+      const float* src = pl < R ? p.Vs + (((size_t)pl * T8 + t) * F + r0) * NB : p.X2t + ((size_t)t * F + r0) * NB;
+      bulk_g2s(data + (size_t)pl * PS + r0 * NB, src, bytes, bars + j);
     }
-    if (j == 0) {   // tile meta data: H_old rows, g, frame_utt, slot multiplicities
-      const int nH = 2 * K, nW = 2 * R;
-      if (tid < nH) cp16(meta + (tid >> 1) * NB + 4 * (tid & 1), p.H + (size_t)(tid >> 1) * NP + col + 4 * (tid & 1));
-      else if (tid < nH + 2) cp16(meta + KMAX * NB + 4 * (tid - nH), p.g + col + 4 * (tid - nH));
-      else if (tid < nH + 4) cp16(meta + (KMAX + 1) * NB + 4 * (tid - nH - 2), p.frame_utt + col + 4 * (tid - nH - 2));
-      else if (tid < nH + 4 + nW) {
-        const int q = tid - nH - 4;
-        cp16(meta + (KMAX + 2 + (q >> 1)) * NB + 4 * (q & 1), p.Vs_w + (size_t)(q >> 1) * NP + col + 4 * (q & 1));
-      }
+  };
+  // all threads: column data of tile t (H_old rows, g, frame_utt, multiplicities) by 16-byte async copies
+  auto issue_meta = [&](int t) {
+    const size_t col = (size_t)t * NB;
+    const int nH = 2 * K, nW = 2 * R;
+    if (tid < nH) cp16(meta + (tid >> 1) * NB + 4 * (tid & 1), p.H + (size_t)(tid >> 1) * NP + col + 4 * (tid & 1));
+    else if (tid < nH + 2) cp16(meta + KMAX * NB + 4 * (tid - nH), p.g + col + 4 * (tid - nH));
+    else if (tid < nH + 4) cp16(meta + (KMAX + 1) * NB + 4 * (tid - nH - 2), p.frame_utt + col + 4 * (tid - nH - 2));
+    else if (tid < nH + 4 + nW) {
+      const int q = tid - nH - 4;
+      cp16(meta + (KMAX + 2 + (q >> 1)) * NB + 4 * (q & 1), p.Vs_w + (size_t)(q >> 1) * NP + col + 4 * (q & 1));
     }
     cp_commit();
   };
 
   // walk the range downwards
-  for (int j = 0; j < NCH; ++j) issue_chunk(t_hi - 1, j);
+  if (warp == 0) for (int j = 0; j < NCH; ++j) issue_chunk(t_hi - 1, j);
+  issue_meta(t_hi - 1);
   int cur_b = -1, cur_fo = -1;
-  for (int t = t_hi - 1; t >= t_lo; --t) {
+  uint32_t par = 0;                                         // phase parity of the chunk barriers for this tile
+  for (int t = t_hi - 1; t >= t_lo; --t, par ^= 1) {
     const bool has_next = t - 1 >= t_lo;
-    cp_wait_dyn(NCH - 1);
+    cp_wait_dyn(0);
     __syncthreads();
     const int b = __float_as_int(meta[(KMAX + 1) * NB]);
-    if (b < 0) {                                            // tile entirely in padding
-      cp_wait_dyn(0);
+    if (b < 0) {                                            // tile entirely in padding: drain its copies, move on
+      for (int j = 0; j < NCH; ++j) mbar_wait(bars + j, par);
       __syncthreads();
       if (tid == 0) p.cost_part[t] = 0.f;
-      if (has_next) for (int j = 0; j < NCH; ++j) issue_chunk(t - 1, j);
+      if (has_next) {
+        if (warp == 0) { fence_proxy_async(); for (int j = 0; j < NCH; ++j) issue_chunk(t - 1, j); }
+        issue_meta(t - 1);
+      }
       continue;
     }
     const bool valid = __float_as_int(meta[(KMAX + 1) * NB + n]) >= 0;
@@ -298,11 +341,11 @@ __global__ void __launch_bounds__(CT, 1) k_cols_v1(ColsArgs p) {
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) num[k] = den[k] = 0.f;
     for (int j = 0; j < NCH; ++j) {
-      if (j > 0) { cp_wait_dyn(NCH - 1 - j); __syncthreads(); }
+      mbar_wait(bars + j, par);
       const int i0 = j * NI / NCH, i1 = (j + 1) * NI / NCH;
-      const float* vs = data + (size_t)(i0 * 32 + fl) * FS + n;
+      const float* vs = data + (size_t)(i0 * 32 + fl) * NB + n;
       const float* wrow = W_s + (i0 * 32 + fl) * KS;
-      for (int i = i0; i < i1; ++i, vs += 32 * FS, wrow += 32 * KS) {
+      for (int i = i0; i < i1; ++i, vs += 32 * NB, wrow += 32 * KS) {
         if (i * 32 + fl < F) {
           float w[KMAX];
 #pragma unroll
@@ -316,14 +359,14 @@ __global__ void __launch_bounds__(CT, 1) k_cols_v1(ColsArgs p) {
           float s1 = 0.f, s2 = 0.f;
           if (RT > 0) {
 #pragma unroll
-            for (int r = 0; r + 1 < RT; r += 2) pair_acc(gg, vb, vs[r * NB], vs[(r + 1) * NB], wgt(r), wgt(r + 1), s1, s2);
-            if (RT & 1) single_acc(gg, vb, vs[(RT - 1) * NB], wgt(RT - 1), s1, s2);
+            for (int r = 0; r + 1 < RT; r += 2) pair_acc(gg, vb, vs[r * PS], vs[(r + 1) * PS], wgt(r), wgt(r + 1), s1, s2);
+            if (RT & 1) single_acc(gg, vb, vs[(RT - 1) * PS], wgt(RT - 1), s1, s2);
           } else {
             int r = 0;
-            for (; r + 1 < R; r += 2) pair_acc(gg, vb, vs[r * NB], vs[(r + 1) * NB], wgt(r), wgt(r + 1), s1, s2);
-            if (r < R) single_acc(gg, vb, vs[r * NB], wgt(r), s1, s2);
+            for (; r + 1 < R; r += 2) pair_acc(gg, vb, vs[r * PS], vs[(r + 1) * PS], wgt(r), wgt(r + 1), s1, s2);
+            if (r < R) single_acc(gg, vb, vs[r * PS], wgt(r), s1, s2);
           }
-          const float a = vs[R * NB] * s2;
+          const float a = vs[R * PS] * s2;
 #pragma unroll
           for (int k = 0; k < KMAX; ++k) { num[k] = fmaf(w[k], a, num[k]); den[k] = fmaf(w[k], s1, den[k]); }
         }
@@ -364,10 +407,12 @@ __global__ void __launch_bounds__(CT, 1) k_cols_v1(ColsArgs p) {
     // ---------------- pass B: Vb = Wun @ H_new (kept for the next E-step, mcem.py:124); g update (:138-142)
     float ng = 0.f, dg = 0.f;
     {
-      const float* vs = data + (size_t)fl * FS + n;
+      const float* vs = data + (size_t)fl * NB + n;
       const float* wrow = W_s + fl * KS;
-      float* vbo = p.Vb + (size_t)fl * NP + (size_t)t * NB + n;
-      for (int i = 0; i < NI; ++i, vs += 32 * FS, wrow += 32 * KS, vbo += (size_t)32 * NP) {
+      const size_t o0 = (size_t)fl * NP + (size_t)t * NB + n;
+      float* vbo = p.Vb + o0;
+      uint32_t* xvo = p.XV != nullptr ? p.XV + o0 : nullptr;
+      for (int i = 0; i < NI; ++i, vs += 32 * NB, wrow += 32 * KS, vbo += (size_t)32 * NP) {
         if (i * 32 + fl < F) {
           float vb = 0.f;
 #pragma unroll
@@ -394,17 +439,18 @@ __global__ void __launch_bounds__(CT, 1) k_cols_v1(ColsArgs p) {
           };
           if (RT > 0) {
 #pragma unroll
-            for (int r = 0; r + 1 < RT; r += 2) pairB(vs[r * NB], vs[(r + 1) * NB], wgt(r), wgt(r + 1));
-            if (RT & 1) singleB(vs[(RT - 1) * NB], wgt(RT - 1));
+            for (int r = 0; r + 1 < RT; r += 2) pairB(vs[r * PS], vs[(r + 1) * PS], wgt(r), wgt(r + 1));
+            if (RT & 1) singleB(vs[(RT - 1) * PS], wgt(RT - 1));
           } else {
             int r = 0;
-            for (; r + 1 < R; r += 2) pairB(vs[r * NB], vs[(r + 1) * NB], wgt(r), wgt(r + 1));
-            if (r < R) singleB(vs[r * NB], wgt(r));
+            for (; r + 1 < R; r += 2) pairB(vs[r * PS], vs[(r + 1) * PS], wgt(r), wgt(r + 1));
+            if (r < R) singleB(vs[r * PS], wgt(r));
           }
-          ng = fmaf(vs[R * NB], t2, ng);
+          ng = fmaf(vs[R * PS], t2, ng);
           dg += t1;
         }
       }
+      (void)xvo;
     }
     ng += __shfl_xor_sync(0xffffffffu, ng, 8);
     ng += __shfl_xor_sync(0xffffffffu, ng, 16);
@@ -427,9 +473,9 @@ __global__ void __launch_bounds__(CT, 1) k_cols_v1(ColsArgs p) {
     float cl = 0.f, cr = 0.f;
     for (int j = 0; j < NCH; ++j) {
       const int i0 = j * NI / NCH, i1 = (j + 1) * NI / NCH;
-      const float* vs = data + (size_t)(i0 * 32 + fl) * FS + n;
+      const float* vs = data + (size_t)(i0 * 32 + fl) * NB + n;
       const float* wrow = W_s + (i0 * 32 + fl) * KS;
-      for (int i = i0; i < i1; ++i, vs += 32 * FS, wrow += 32 * KS) {
+      for (int i = i0; i < i1; ++i, vs += 32 * NB, wrow += 32 * KS) {
         if (i * 32 + fl < F) {
           float vb = 0.f;
 #pragma unroll
@@ -451,19 +497,22 @@ __global__ void __launch_bounds__(CT, 1) k_cols_v1(ColsArgs p) {
           };
           if (RT > 0) {
 #pragma unroll
-            for (int r = 0; r + 1 < RT; r += 2) pairC(vs[r * NB], vs[(r + 1) * NB], wgt(r), wgt(r + 1));
-            if (RT & 1) singleC(vs[(RT - 1) * NB], wgt(RT - 1));
+            for (int r = 0; r + 1 < RT; r += 2) pairC(vs[r * PS], vs[(r + 1) * PS], wgt(r), wgt(r + 1));
+            if (RT & 1) singleC(vs[(RT - 1) * PS], wgt(RT - 1));
           } else {
             int r = 0;
-            for (; r + 1 < R; r += 2) pairC(vs[r * NB], vs[(r + 1) * NB], wgt(r), wgt(r + 1));
-            if (r < R) singleC(vs[r * NB], wgt(r));
+            for (; r + 1 < R; r += 2) pairC(vs[r * PS], vs[(r + 1) * PS], wgt(r), wgt(r + 1));
+            if (r < R) singleC(vs[r * PS], wgt(r));
           }
           cl += sl;
-          cr = fmaf(vs[R * NB], sr, cr);
+          cr = fmaf(vs[R * PS], sr, cr);
         }
       }
       __syncthreads();                                      // chunk j is free (and `red` of pass B is consumed)
-      if (has_next) issue_chunk(t - 1, j);
+      if (has_next) {
+        if (warp == 0) { fence_proxy_async(); issue_chunk(t - 1, j); }
+        if (j == 0) issue_meta(t - 1);
+      }
     }
     float cs = valid ? fmaf(cl, 0.6931471805599453f, cr) : 0.f;
 #pragma unroll
@@ -487,18 +536,22 @@ int32_t launch_cols(const ColsArgs& a, size_t smem, int grid, cudaStream_t st) {
   return check_launch("k_cols_v1");
 }
 
+template <int KMAX, int RT>
+int32_t launch_w(const gvn_batch* b, int R, cudaStream_t st) {
+  const size_t smem = (size_t)WS * w_stage_floats(b->K, R) * 4;
+  cudaError_t e = cudaFuncSetAttribute(k_w_v2<KMAX, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return fail(GVN_E_CUDA, "k_w_v2 smem attr (%zu B): %s", smem, cudaGetErrorString(e));
+  dim3 gw((b->F + WROWS - 1) / WROWS, b->B);
+  k_w_v2<KMAX, RT><<<gw, WT, smem, st>>>(b->F, b->K, b->NP, R, b->frame_off, b->n_frames, b->X2t, b->Vs, b->Vs_w, b->g, b->H, b->W, b->Wun);
+  return check_launch("k_w_v2");
+}
+
 inline int kmax_of(int K) { return (K + 3) / 4 * 4; }
 inline int ks_of(int K) { int ks = kmax_of(K); return (ks % 16 == 0) ? ks + 4 : ks; }
-inline int rs_of(int R) { return (R + 1) | 1; }
 
 template <int KMAX>
 int32_t launch_v1_k(const gvn_batch* b, int R, const ColsArgs& a, size_t smem, int grid, cudaStream_t st) {
-  dim3 gw((b->F + CT / 32 - 1) / (CT / 32), b->B);
-  if (R == 10)
-    k_w_v1<KMAX, 10><<<gw, CT, 0, st>>>(b->F, b->K, b->NP, R, b->frame_off, b->n_frames, b->X2, b->Vs, b->Vs_w, b->Vb, b->g, b->H, b->W, b->Wun);
-  else
-    k_w_v1<KMAX, 0><<<gw, CT, 0, st>>>(b->F, b->K, b->NP, R, b->frame_off, b->n_frames, b->X2, b->Vs, b->Vs_w, b->Vb, b->g, b->H, b->W, b->Wun);
-  int32_t rc = check_launch("k_w_v1");
+  int32_t rc = R == 10 ? launch_w<KMAX, 10>(b, R, st) : launch_w<KMAX, 0>(b, R, st);
   if (rc) return rc;
   return R == 10 ? launch_cols<KMAX, 10>(a, smem, grid, st) : launch_cols<KMAX, 0>(a, smem, grid, st);
 }
@@ -507,21 +560,22 @@ int32_t launch_v1_k(const gvn_batch* b, int R, const ColsArgs& a, size_t smem, i
 
 // true when variant 1 can run this shape (the tile block must fit in shared memory)
 bool mstep_v1_supported(const gvn_batch* b, int R) {
-  if (b->K > 16) return false;
-  const size_t bytes = cols_smem_floats(b->F, ks_of(b->K), R, rs_of(R), kmax_of(b->K)) * 4;
-  return bytes <= 227 * 1024;
+  if (b->K > 16 || b->X2t == nullptr) return false;
+  const size_t bytes = cols_smem_floats(b->F, ks_of(b->K), R, kmax_of(b->K)) * 4;
+  const size_t wbytes = (size_t)WS * w_stage_floats(b->K, R) * 4;
+  return bytes <= 227 * 1024 && wbytes <= 227 * 1024;
 }
 
 int32_t launch_mstep_v1(const gvn_batch* b, int R, float* cost_part, cudaStream_t st) {
   const int KMAX = kmax_of(b->K);
   ColsArgs a;
-  a.F = b->F; a.K = b->K; a.KS = ks_of(b->K); a.NP = b->NP; a.R = R; a.RS = rs_of(R); a.B = b->B;
+  a.F = b->F; a.K = b->K; a.KS = ks_of(b->K); a.NP = b->NP; a.R = R; a.B = b->B;
   a.ntiles = b->NP / NB;
   const int NI = (b->F + 31) / 32;
   a.nchunk = NI < MAXCH ? NI : MAXCH;
-  a.frame_utt = b->frame_utt; a.frame_off = b->frame_off; a.X2 = b->X2; a.Vs = b->Vs; a.Vs_w = b->Vs_w;
-  a.Vb = b->Vb; a.g = b->g; a.H = b->H; a.Wun = b->Wun; a.W = b->W; a.cost_part = cost_part;
-  const size_t smem = cols_smem_floats(b->F, a.KS, R, a.RS, KMAX) * 4;
+  a.frame_utt = b->frame_utt; a.frame_off = b->frame_off; a.X2t = b->X2t; a.Vs = b->Vs; a.Vs_w = b->Vs_w;
+  a.Vb = b->Vb; a.g = b->g; a.H = b->H; a.Wun = b->Wun; a.W = b->W; a.cost_part = cost_part; a.XV = nullptr;
+  const size_t smem = cols_smem_floats(b->F, a.KS, R, KMAX) * 4;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

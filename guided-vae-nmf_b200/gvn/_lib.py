@@ -23,7 +23,7 @@ class GvnBatch(C.Structure):
     _fields_ = [("B", _i), ("F", _i), ("K", _i), ("L", _i), ("NP", _i), ("R_cap", _i),
                 ("frame_off", _p), ("n_frames", _p), ("frame_utt", _p),
                 ("X2", _p), ("Xc", _p), ("W", _p), ("Wun", _p), ("H", _p), ("g", _p),
-                ("Vb", _p), ("Z", _p), ("Vs", _p), ("yproj", _p), ("Vs_w", _p), ("XV", _p)]
+                ("Vb", _p), ("Z", _p), ("Vs", _p), ("yproj", _p), ("Vs_w", _p), ("XV", _p), ("X2t", _p)]
 
 
 class GvnNoise(C.Structure):

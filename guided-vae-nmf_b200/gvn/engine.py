@@ -131,7 +131,8 @@ class Batch:
         self.g = torch.ones(NP, **f32)
         self.Vb = torch.ones(F, NP, **f32)
         self.Z = torch.zeros(L, NP, **f32)
-        self.Vs = torch.zeros(R_cap, F, NP, **f32)          # slot form, see include/gvn.h
+        self.Vs = torch.zeros(R_cap, NP // 8, F, 8, **f32)  # slot form in column-tile order, see include/gvn.h
+        self.X2t = torch.ones(NP // 8, F, 8, **f32)
         self.Vs_w = torch.zeros(R_cap, NP, **f32)
         self.XV = torch.empty(F, NP, dtype=torch.int32, device=device)
         self.yproj = torch.zeros(GVN_HIDDEN, NP, **f32)
@@ -141,7 +142,7 @@ class Batch:
     def struct(self):
         s = GvnBatch()
         s.B, s.F, s.K, s.L, s.NP, s.R_cap = self.B, self.F, self.K, self.L, self.NP, self.R_cap
-        for name in ("frame_off", "n_frames", "frame_utt", "X2", "Xc", "W", "Wun", "H", "g", "Vb", "Z", "Vs", "yproj", "Vs_w", "XV"):
+        for name in ("frame_off", "n_frames", "frame_utt", "X2", "Xc", "W", "Wun", "H", "g", "Vb", "Z", "Vs", "yproj", "Vs_w", "XV", "X2t"):
             t = getattr(self, name)
             setattr(s, name, 0 if t is None else t.data_ptr())
         self._struct = s
@@ -166,8 +167,15 @@ class Batch:
         w = self.Vs_w[:R]
         idx = torch.arange(R, device=w.device).unsqueeze(1) * (w > 0)
         src = torch.cummax(idx, dim=0).values                              # (R, NP)
-        out = torch.gather(self.Vs[:R], 0, src.unsqueeze(1).expand(R, self.F, self.NP))
+        vs = self.Vs[:R].permute(0, 2, 1, 3).reshape(R, self.F, self.NP)    # column tiles -> (R,F,NP)
+        out = torch.gather(vs, 0, src.unsqueeze(1).expand(R, self.F, self.NP))
         return out if b is None else out[..., self.cols(b)]
+
+    def set_samples(self, vs, w=None):
+        """(R,F,NP) sample tensor -> the column-tile slot form (tests)."""
+        R = vs.shape[0]
+        self.Vs[:R].copy_(vs.reshape(R, self.F, self.NP // 8, 8).permute(0, 2, 1, 3))
+        self.Vs_w[:R].copy_(torch.ones(R, self.NP, device=vs.device) if w is None else w)
 
 
 # --------------------------------------------------------------------------------------

@@ -30,7 +30,11 @@
  *    Vb   [F][NP]  f32   noise variance W@H        (mcem.py:82; NOT refreshed after the
  *                                                   normalisation, as in mcem.py:124-133)
  *    Z    [L][NP]  f32   current latent state      (mcem.py:215, 319)
- *    Vs   [R][F][NP] f32 speech variance of the kept samples (mcem.py:307), slot form: slot r
+ *    Vs   [R][NP/8][F][8] f32 speech variance of the kept samples (mcem.py:307) in column-tile
+ *                        order: element (r, f, n) lives at ((r*(NP/8) + n/8)*F + f)*8 + n%8, so the
+ *                        F x 8 block of one 8-frame column tile is contiguous (16 KB at F=513) --
+ *                        what the M-step stages per tile -- and a row of it is one 32-byte sector.
+ *                        Slot form: slot r
  *                        holds the decoder output of the PROPOSAL of kept step r (slot 0: the state
  *                        after the burn-in) and
  *    Vs_w [R][NP]    f32 its multiplicity: 0 when that proposal was rejected, 1 + (number of
@@ -39,6 +43,7 @@
  *                        equals sum_slot Vs_w[slot] * phi(Vs[slot]); nothing is ever copied.
  *                        sum_slot Vs_w[slot][n] == R for every frame.
  *    XV   [F][NP]    u32 scratch of the tensor-core chain: bf16(X2) << 16 | bf16(Vb)
+ *    X2t  [NP/8][F][8] f32 X2 in column-tile order (built by gvn_init_nmf; read by gvn_mstep)
  *    yproj[HID][NP] f32  b1 + W1[:, L:] @ y  -- the label part of the decoder's first layer,
  *                        constant per utterance (mcem.py:242 concatenates y every step)
  */
@@ -92,6 +97,7 @@ typedef struct gvn_batch {
   const float* yproj;
   float* Vs_w;
   uint32_t* XV;                   /* may be NULL when only GVN_PREC_FP32 is used            */
+  float* X2t;
 } gvn_batch;
 
 /* random input of one Metropolis-Hastings chain (mcem.py:257 randn(L,N), :271 rand(N)).

@@ -32,8 +32,8 @@ def test_library_loads_and_exports_every_declared_symbol():
 
 
 def test_struct_layouts_match_header():
-    # 6 int32 + 15 pointers; noise: 3 pointers + 2 u64; trace: 4 pointers
-    assert ctypes.sizeof(_lib.GvnBatch) == 6 * 4 + 15 * 8
+    # 6 int32 + 16 pointers; noise: 3 pointers + 2 u64; trace: 4 pointers
+    assert ctypes.sizeof(_lib.GvnBatch) == 6 * 4 + 16 * 8
     assert ctypes.sizeof(_lib.GvnNoise) == 5 * 8
     assert ctypes.sizeof(_lib.GvnTrace) == 4 * 8
 

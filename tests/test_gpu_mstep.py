@@ -12,19 +12,22 @@ def _random_batch(n_frames, F, K, L, R, seed):
     from gvn import engine as E
     g = torch.Generator(device="cuda").manual_seed(seed)
     b = E.Batch(n_frames, F, K, L, R, "cuda:0", with_complex=False)
-    E.init_nmf(b, 1e-8, generator=g)
     b.X2.copy_(torch.rand(F, b.NP, generator=g, device="cuda") * 3 + 1e-3)
-    b.Vs.copy_(torch.exp(torch.randn(R, F, b.NP, generator=g, device="cuda") * 2 - 1))
+    E.init_nmf(b, 1e-8, generator=g)                       # also builds the column-tile copy of X2
+    vs = torch.exp(torch.randn(R, F, b.NP, generator=g, device="cuda") * 2 - 1)
     b.g.copy_(torch.rand(b.NP, generator=g, device="cuda") + 0.5)
     b.H.copy_(torch.rand(K, b.NP, generator=g, device="cuda") + 1e-3)
     b.W.copy_(torch.rand(b.B, F, K, generator=g, device="cuda") + 1e-3)
+    for i in range(b.B):                                   # Vb is the product W @ H, as after any M-step
+        b.Vb[:, b.cols(i)] = b.W[i] @ b.H[:, b.cols(i)]
     # slot multiplicities (include/gvn.h): slot 0 always live, some slots dead (rejected proposals)
     w = torch.randint(0, 3, (R, b.NP), generator=g, device="cuda").float()
     w[0] += 1
-    b.Vs_w.copy_(w)
+    b.Vs_w[:R].copy_(w)
     # poison the padding columns of Vs: they must never be read into a result
     pad = b.frame_utt < 0
-    b.Vs[:, :, pad] = float("nan")
+    vs[:, :, pad] = float("nan")
+    b.set_samples(vs, b.Vs_w[:R].clone())
     return b
 
 
