@@ -308,14 +308,17 @@ __global__ void k_init_nmf_cols(int F, int K, int NP, const int32_t* __restrict_
 
 }  // namespace
 
-size_t mstep_workspace_bytes(const gvn_batch* b) { return (size_t)b->B * b->K * sizeof(float); }
+size_t mstep_v1_workspace_bytes(const gvn_batch*);
+size_t mstep_workspace_bytes(const gvn_batch* b) { return round_up((size_t)b->B * b->K, 64) * sizeof(float) + mstep_v1_workspace_bytes(b) + 256; }
 
 bool mstep_v1_supported(const gvn_batch*, int);
-int32_t launch_mstep_v1(const gvn_batch*, int, float*, cudaStream_t);
+size_t mstep_v1_workspace_bytes(const gvn_batch*);
+int32_t launch_mstep_v1(const gvn_batch*, int, float*, float*, cudaStream_t);
 
 int32_t launch_mstep(const gvn_batch* b, int R, float* cost_part, void* workspace, int variant, cudaStream_t st) {
   // variant 0: reference schedule (any shape); variant 1 (default when the tile fits in shared memory): mstep_v1.cu
-  if (variant != 0 && mstep_v1_supported(b, R)) return launch_mstep_v1(b, R, cost_part, st);
+  if (variant != 0 && mstep_v1_supported(b, R))
+    return launch_mstep_v1(b, R, cost_part, reinterpret_cast<float*>(workspace) + round_up((size_t)b->B * b->K, 64), st);   // 256-byte aligned
   float* cnorm = reinterpret_cast<float*>(workspace);
   dim3 gw((b->F + MS_WARPS - 1) / MS_WARPS, b->B);
   const int ntiles = b->NP / MS_TILE;

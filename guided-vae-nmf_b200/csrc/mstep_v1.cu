@@ -87,6 +87,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (spins > (1u << 26)) __trap();       // a protocol bug must surface as an error, not a hang
   }
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(s_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s_u32(dst)),
                "l"(src), "r"(bytes), "r"(s_u32(bar)) : "memory");
@@ -94,14 +97,31 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
+// ------------------------------------------------------------------ column data in tile order
+// Mt[t][K+1+R][8]: rows 0..K-1 = H, row K = g, rows K+1.. = slot multiplicities of the 8 frames of
+// column tile t -- one contiguous block per tile, so a stage needs ONE copy for all of it.
+__global__ void __launch_bounds__(256) k_tile_meta(int K, int R, int NP, const float* __restrict__ H, const float* __restrict__ g,
+                                                   const float* __restrict__ Vs_w, float* __restrict__ Mt) {
+  const int MR = K + 1 + R;
+  const size_t total = (size_t)MR * NP;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int n8 = (int)(i & 7), m = (int)((i >> 3) % MR);
+    const size_t t = (i >> 3) / MR, col = t * NB + n8;
+    Mt[i] = m < K ? H[(size_t)m * NP + col] : (m == K ? g[col] : Vs_w[(size_t)(m - K - 1) * NP + col]);
+  }
+}
+
 // ------------------------------------------------------------------ W update (mcem.py:105-110)
-// One CTA per (utterance, block of 64 frequency rows); thread = (row, column n of an 8-frame
-// tile).  The [rows][8] blocks of the R sample slots and of X2 (column-tile order: contiguous
-// rows*32 bytes each) stream through a ring of WS stages filled by bulk async copies, so the
-// bytes in flight live in shared memory, not in registers.  Vb of the reference is W @ H here
-// (the stored Vb is the same product before the normalisation, mcem.py:124-133).
+// One CTA per (utterance, block of 64 frequency rows); compute thread = (row, column n of an
+// 8-frame tile).  The [rows][8] blocks of the R sample slots and of X2 (column-tile order:
+// contiguous rows*32 bytes each) plus the tile's column data stream through a ring of WS stages
+// filled by bulk async copies from a dedicated producer warp, so the bytes in flight live in
+// shared memory, not in registers, and the compute warps never meet at a CTA-wide barrier.
+// Vb of the reference is W @ H here (the stored Vb is the same product before the
+// normalisation, mcem.py:124-133).
 constexpr int WROWS = 64;             // frequency rows per CTA
-constexpr int WT = WROWS * NB;        // 512 threads
+constexpr int WCT = WROWS * NB;       // 512 compute threads
+constexpr int WT = WCT + 32;          // + producer warp
 constexpr int WS = 4;                 // ring stages (two CTAs per SM: 8 stages of ~23 KB in flight)
 
 // floats of one ring stage: (R+1) planes of [WROWS][NB] + column data (H rows, g, multiplicities)
@@ -110,48 +130,48 @@ __host__ __device__ inline int w_stage_floats(int K, int R) { return ((R + 1) * 
 template <int KMAX, int RT>
 __global__ void __launch_bounds__(WT, 2) k_w_v2(int F, int K, int NP, int R_rt, const int32_t* __restrict__ frame_off,
                                                 const int32_t* __restrict__ n_frames, const float* __restrict__ X2t,
-                                                const float* __restrict__ Vs, const float* __restrict__ Vs_w,
-                                                const float* __restrict__ g, const float* __restrict__ H,
+                                                const float* __restrict__ Vs, const float* __restrict__ Mt,
                                                 const float* __restrict__ W, float* __restrict__ Wun) {
   extern __shared__ __align__(128) float smw[];             // [WS][stage]
-  __shared__ __align__(8) uint64_t full[WS];
+  __shared__ __align__(8) uint64_t full[WS], empty[WS];
   const int R = RT > 0 ? RT : R_rt;
-  const int tid = threadIdx.x, n = tid & (NB - 1), rl = tid >> 3;
-  const int b = blockIdx.y, f0 = blockIdx.x * WROWS, f = f0 + rl;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int b = blockIdx.y, f0 = blockIdx.x * WROWS;
   const int rows = min(WROWS, F - f0);
-  const bool rowok = rl < rows;
   const int n_begin = frame_off[b], N = n_frames[b];
   const int ntile = (N + NB - 1) / NB, t0 = n_begin / NB, T8 = NP / NB;
   constexpr int PSt = WROWS * NB;                           // plane stride inside a stage (floats)
   const int MO = (R + 1) * PSt;                             // offset of the column data inside a stage
+  const int MR = K + 1 + R;
   const int SSt = w_stage_floats(K, R);
-  const uint32_t blk = (uint32_t)rows * NB * 4;             // bytes of one plane block
-  const int ncopy = (R + 1) + (K + 1 + R);
 
   if (tid == 0) {
-    for (int s = 0; s < WS; ++s) mbar_init(full + s, 1);
+    for (int s = 0; s < WS; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, WCT / 32); }
     fence_mbar_init();
   }
   __syncthreads();
-  // warp 0: lane i issues copy i of tile ti into stage ti % WS (plane blocks, then 32-byte column rows)
-  auto issue = [&](int ti) {
-    const int s = ti % WS, lane = tid;
-    float* dst = smw + (size_t)s * SSt;
-    const size_t col = (size_t)n_begin + (size_t)ti * NB;
-    if (lane == 0) mbar_expect_tx(full + s, blk * (R + 1) + (uint32_t)(K + 1 + R) * NB * 4);
-    __syncwarp();
-    for (int c = lane; c < ncopy; c += 32) {
-      if (c < R) bulk_g2s(dst + c * PSt, Vs + (((size_t)c * T8 + t0 + ti) * F + f0) * NB, blk, full + s);
-      else if (c == R) bulk_g2s(dst + R * PSt, X2t + ((size_t)(t0 + ti) * F + f0) * NB, blk, full + s);
-      else {
-        const int m = c - R - 1;                            // 0..K-1: H rows, K: g, K+1..: multiplicities
-        const float* src = m < K ? H + (size_t)m * NP + col : (m == K ? g + col : Vs_w + (size_t)(m - K - 1) * NP + col);
-        bulk_g2s(dst + MO + m * NB, src, NB * 4, full + s);
+
+  if (tid >= WCT) {
+    // ================= producer warp: lane p copies plane p, lane R+1 the column data =================
+    const uint32_t blk = (uint32_t)rows * NB * 4;
+    for (int ti = 0; ti < ntile; ++ti) {
+      const int s = ti % WS;
+      if (ti >= WS) mbar_wait(empty + s, ((ti / WS) - 1) & 1);
+      float* dst = smw + (size_t)s * SSt;
+      if (lane == 0) mbar_expect_tx(full + s, blk * (R + 1) + (uint32_t)MR * NB * 4);
+      __syncwarp();
+      for (int c = lane; c <= R + 1; c += 32) {
+        if (c < R) bulk_g2s(dst + c * PSt, Vs + (((size_t)c * T8 + t0 + ti) * F + f0) * NB, blk, full + s);
+        else if (c == R) bulk_g2s(dst + R * PSt, X2t + ((size_t)(t0 + ti) * F + f0) * NB, blk, full + s);
+        else bulk_g2s(dst + MO, Mt + (size_t)(t0 + ti) * MR * NB, (uint32_t)MR * NB * 4, full + s);
       }
     }
-  };
-  if (tid < 32) for (int ti = 0; ti < WS && ti < ntile; ++ti) issue(ti);
+    return;
+  }
 
+  // ================= compute warps =================
+  const int n = tid & (NB - 1), rl = tid >> 3, f = f0 + rl;
+  const bool rowok = rl < rows;
   float w[KMAX], num[KMAX], den[KMAX];
 #pragma unroll
   for (int k = 0; k < KMAX; ++k) { w[k] = (k < K && rowok) ? W[((size_t)b * F + f) * K + k] : 0.f; num[k] = den[k] = 0.f; }
@@ -183,8 +203,8 @@ __global__ void __launch_bounds__(WT, 2) k_w_v2(int F, int K, int NP, int R_rt, 
 #pragma unroll
       for (int k = 0; k < KMAX; ++k) if (k < K) { const float h = mt[k * NB]; num[k] = fmaf(a, h, num[k]); den[k] = fmaf(s1, h, den[k]); }
     }
-    __syncthreads();                                        // stage s is free
-    if (tid < 32 && ti + WS < ntile) { fence_proxy_async(); issue(ti + WS); }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty + s);                  // this warp is done with stage s
   }
   // reduce over the 8 columns of the tile (adjacent lanes), lane n == 0 writes the row
 #pragma unroll
@@ -206,36 +226,45 @@ __global__ void __launch_bounds__(WT, 2) k_w_v2(int F, int K, int NP, int R_rt, 
 struct ColsArgs {
   int F, K, KS, NP, R, B, ntiles, nchunk;
   const int32_t* frame_utt; const int32_t* frame_off;
-  const float* X2t; const float* Vs; const float* Vs_w;
-  float* Vb; float* g; float* H; const float* Wun; float* W; float* cost_part; uint32_t* XV;
+  const float* X2t; const float* Vs; const float* Mt;
+  float* Vb; float* g; float* H; const float* Wun; float* W; float* cost_part;
 };
 
+constexpr int CCT = 256;              // compute threads of the column sweep
+constexpr int CTT = CCT + 32;         // + producer warp
+
 // shared memory (floats): data[(R+1)][F][NB] (plane R = X2) | W_s[F][KS] | red[8][2*KMAX][NB] |
-// red2[2*KMAX][NB] | Hn_s[KMAX][NB] | meta[(KMAX+2+R)][NB] | wts_s[R][NB] | cn_s[KMAX] | misc[32] | bars[MAXCH]
-__host__ __device__ inline size_t cols_smem_floats(int F, int KS, int R, int KMAX) {
+// red2[2*KMAX][NB] | Hn_s[KMAX][NB] | meta[K+1+R][NB] + fu[NB] | cn_s[KMAX] | misc[32] | bars
+__host__ __device__ inline size_t cols_smem_floats(int F, int KS, int K, int R, int KMAX) {
   return (size_t)(R + 1) * F * NB + (size_t)F * KS + (size_t)8 * 2 * KMAX * NB + (size_t)2 * KMAX * NB + (size_t)KMAX * NB +
-         (size_t)(KMAX + 2 + R) * NB + (size_t)R * NB + KMAX + 32 + 2 * MAXCH + 4;
+         (size_t)(K + 1 + R + 1) * NB + KMAX + 32 + 2 * (2 * MAXCH + 2) + 4 + 2 * (MAXCH + 1);
 }
 
+__device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
 template <int KMAX, int RT>
-__global__ void __launch_bounds__(CT, 1) k_cols_v1(ColsArgs p) {
+__global__ void __launch_bounds__(CTT, 1) k_cols_v1(ColsArgs p) {
   extern __shared__ __align__(128) float sm[];
   const int F = p.F, K = p.K, KS = p.KS, NP = p.NP;
   const int R = RT > 0 ? RT : p.R;
+  const int MR = K + 1 + R;
   const int PS = F * NB;                                    // plane stride (floats); a plane is one bulk-contiguous block
   float* data = sm;
   float* W_s = data + (size_t)(R + 1) * PS;
   float* red = W_s + (size_t)F * KS;
   float* red2 = red + 8 * 2 * KMAX * NB;
   float* Hn_s = red2 + 2 * KMAX * NB;
-  float* meta = Hn_s + KMAX * NB;                           // H_old [KMAX][NB] | g [NB] | frame_utt [NB] | Vs_w [R][NB]
-  float* wts_s = meta + (KMAX + 2 + R) * NB;                // [R][NB] multiplicities of the current tile
-  float* cn_s = wts_s + R * NB;
+  float* meta = Hn_s + KMAX * NB;                           // H_old [K][NB] | g [NB] | Vs_w [R][NB]   (one bulk copy)
+  float* cn_s = meta + (MR + 1) * NB;
   float* misc = cn_s + KMAX;
-  uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(misc + 32) + 7) & ~(uintptr_t)7);   // [MAXCH]
+  uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(misc + 32) + 7) & ~(uintptr_t)7);
+  uint64_t* full = bars;                                    // [MAXCH] chunk j of the tile has landed
+  uint64_t* empty = bars + MAXCH;                           // [MAXCH] chunk j has been consumed by the cost pass
+  uint64_t* mfull = bars + 2 * MAXCH;                       // column data landed
+  uint64_t* mempty = mfull + 1;                             // column data consumed
+  int* cb = reinterpret_cast<int*>(bars + 2 * MAXCH + 2);   // [NCH+1] chunk boundaries in units of 32 rows
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int n = tid & (NB - 1), fl = tid >> 3;              // column of the tile, frequency lane (0..31)
   const int NI = (F + 31) / 32, NCH = p.nchunk, T8 = NP / NB;
 
   // contiguous tile range of this CTA, walked from the END of the batch: the W sweep that ran
@@ -247,93 +276,86 @@ __global__ void __launch_bounds__(CT, 1) k_cols_v1(ColsArgs p) {
   if (t_hi <= 0) return;
 
   if (tid == 0) {
-    for (int j = 0; j < NCH; ++j) mbar_init(bars + j, 1);
+    for (int j = 0; j < NCH; ++j) { mbar_init(full + j, 1); mbar_init(empty + j, CCT / 32); }
+    mbar_init(mfull, 1);
+    mbar_init(mempty, CCT / 32);
+    for (int j = 0; j <= NCH; ++j) cb[j] = j * NI / NCH;
     fence_mbar_init();
   }
   __syncthreads();
 
-  // warp 0: rows [r0, r1) of every plane of tile t, one bulk copy per plane (lane = plane)
-  auto issue_chunk = [&](int t, int j) {
-    const int i0 = j * NI / NCH, i1 = (j + 1) * NI / NCH;
-    const int r0 = i0 * 32, r1 = min(i1 * 32, F);
-    const uint32_t bytes = (uint32_t)(r1 - r0) * NB * 4;
-    if (lane == 0) mbar_expect_tx(bars + j, bytes * (R + 1));
-    __syncwarp();
-    for (int pl = lane; pl <= R; pl += 32) {
-      const float* src = pl < R ? p.Vs + (((size_t)pl * T8 + t) * F + r0) * NB : p.X2t + ((size_t)t * F + r0) * NB;
-      bulk_g2s(data + (size_t)pl * PS + r0 * NB, src, bytes, bars + j);
-    }
-  };
-  // all threads: column data of tile t (H_old rows, g, frame_utt, multiplicities) by 16-byte async copies
-  auto issue_meta = [&](int t) {
-    const size_t col = (size_t)t * NB;
-    const int nH = 2 * K, nW = 2 * R;
-    if (tid < nH) cp16(meta + (tid >> 1) * NB + 4 * (tid & 1), p.H + (size_t)(tid >> 1) * NP + col + 4 * (tid & 1));
-    else if (tid < nH + 2) cp16(meta + KMAX * NB + 4 * (tid - nH), p.g + col + 4 * (tid - nH));
-    else if (tid < nH + 4) cp16(meta + (KMAX + 1) * NB + 4 * (tid - nH - 2), p.frame_utt + col + 4 * (tid - nH - 2));
-    else if (tid < nH + 4 + nW) {
-      const int q = tid - nH - 4;
-      cp16(meta + (KMAX + 2 + (q >> 1)) * NB + 4 * (q & 1), p.Vs_w + (size_t)(q >> 1) * NP + col + 4 * (q & 1));
-    }
-    cp_commit();
-  };
-
-  // walk the range downwards
-  if (warp == 0) for (int j = 0; j < NCH; ++j) issue_chunk(t_hi - 1, j);
-  issue_meta(t_hi - 1);
-  int cur_b = -1, cur_fo = -1;
-  uint32_t par = 0;                                         // phase parity of the chunk barriers for this tile
-  for (int t = t_hi - 1; t >= t_lo; --t, par ^= 1) {
-    const bool has_next = t - 1 >= t_lo;
-    cp_wait_dyn(0);
-    __syncthreads();
-    const int b = __float_as_int(meta[(KMAX + 1) * NB]);
-    if (b < 0) {                                            // tile entirely in padding: drain its copies, move on
-      for (int j = 0; j < NCH; ++j) mbar_wait(bars + j, par);
-      __syncthreads();
-      if (tid == 0) p.cost_part[t] = 0.f;
-      if (has_next) {
-        if (warp == 0) { fence_proxy_async(); for (int j = 0; j < NCH; ++j) issue_chunk(t - 1, j); }
-        issue_meta(t - 1);
+  if (tid >= CCT) {
+    // ================= producer warp: lane = plane; one bulk copy per plane and chunk =================
+    uint32_t it = 0;
+    for (int t = t_hi - 1; t >= t_lo; --t, ++it) {
+      if (it > 0) mbar_wait(mempty, (it - 1) & 1);
+      if (lane == 0) {
+        mbar_expect_tx(mfull, (uint32_t)MR * NB * 4);
+        bulk_g2s(meta, p.Mt + (size_t)t * MR * NB, (uint32_t)MR * NB * 4, mfull);
       }
+      for (int j = 0; j < NCH; ++j) {
+        if (it > 0) mbar_wait(empty + j, (it - 1) & 1);
+        const int r0 = cb[j] * 32, r1 = min(cb[j + 1] * 32, F);
+        const uint32_t bytes = (uint32_t)(r1 - r0) * NB * 4;
+        if (lane == 0) mbar_expect_tx(full + j, bytes * (R + 1));
+        __syncwarp();
+        for (int pl = lane; pl <= R; pl += 32) {
+          const float* src = pl < R ? p.Vs + (((size_t)pl * T8 + t) * F + r0) * NB : p.X2t + ((size_t)t * F + r0) * NB;
+          bulk_g2s(data + (size_t)pl * PS + r0 * NB, src, bytes, full + j);
+        }
+      }
+    }
+    return;
+  }
+
+  // ================= compute warps =================
+  const int n = tid & (NB - 1), fl = tid >> 3;              // column of the tile, frequency lane (0..31)
+  int cur_b = -1, cur_fo = -1;
+  uint32_t par = 0;                                         // phase parity of the barriers for this tile
+  for (int t = t_hi - 1; t >= t_lo; --t, par ^= 1) {
+    mbar_wait(mfull, par);
+    const int b = p.frame_utt[(size_t)t * NB];              // tiles never straddle utterances (32-frame alignment)
+    if (b < 0) {                                            // tile entirely in padding: drain its copies, move on
+      for (int j = 0; j < NCH; ++j) mbar_wait(full + j, par);
+      if (tid == 0) p.cost_part[t] = 0.f;
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(mempty); for (int j = 0; j < NCH; ++j) mbar_arrive(empty + j); }
       continue;
     }
-    const bool valid = __float_as_int(meta[(KMAX + 1) * NB + n]) >= 0;
-    const float gg = meta[KMAX * NB + n];
+    const bool valid = p.frame_utt[(size_t)t * NB + n] >= 0;
+    const float gg = meta[K * NB + n];
     float hk[KMAX];
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) hk[k] = (k < K) ? meta[k * NB + n] : 0.f;
-    // multiplicities of the slots of this column: registers when R is a compile-time constant,
-    // a private shared copy otherwise (`meta` is overwritten by the next tile's copies)
+    // multiplicities of the slots of this column: registers when R is a compile-time constant
     float wr[RT > 0 ? RT : 1];
     if (RT > 0) {
 #pragma unroll
-      for (int r = 0; r < RT; ++r) wr[r] = meta[(KMAX + 2 + r) * NB + n];
-    } else {
-      for (int i = tid; i < R * NB; i += CT) wts_s[i] = meta[(KMAX + 2) * NB + i];
+      for (int r = 0; r < RT; ++r) wr[r] = meta[(K + 1 + r) * NB + n];
     }
-    const float* wsm = wts_s + n;
+    const float* wsm = meta + (K + 1) * NB + n;
     auto wgt = [&](int r) -> float { return RT > 0 ? wr[RT > 0 ? r : 0] : wsm[r * NB]; };
 
     if (b != cur_b) {                                       // new utterance: dictionary -> smem, column norms
       cur_b = b;
       cur_fo = p.frame_off[b];
+      bar_compute();                                        // everybody is done with the previous W_s
       const float* wsrc = p.Wun + (size_t)b * F * K;
-      for (int i = tid; i < F * K; i += CT) { const int ff = i / K; W_s[ff * KS + (i - ff * K)] = __ldg(wsrc + i); }
-      if (KS > K) for (int i = tid; i < F * (KS - K); i += CT) { const int ff = i / (KS - K); W_s[ff * KS + K + (i - ff * (KS - K))] = 0.f; }
-      __syncthreads();
-      for (int k = warp; k < K; k += CT / 32) {             // c_k = sum_f |W_fk|  (mcem.py:128)
+      for (int i = tid; i < F * K; i += CCT) { const int ff = i / K; W_s[ff * KS + (i - ff * K)] = __ldg(wsrc + i); }
+      if (KS > K) for (int i = tid; i < F * (KS - K); i += CCT) { const int ff = i / (KS - K); W_s[ff * KS + K + (i - ff * (KS - K))] = 0.f; }
+      bar_compute();
+      for (int k = warp; k < K; k += CCT / 32) {            // c_k = sum_f |W_fk|  (mcem.py:128)
         float s = 0.f;
         for (int ff = lane; ff < F; ff += 32) s += fabsf(W_s[ff * KS + k]);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         if (lane == 0) cn_s[k] = s;
       }
+      bar_compute();
     }
-    __syncthreads();                                        // W_s, cn_s, wts_s visible
     if (t * NB == cur_fo) {                                 // the first tile of an utterance writes W / c (mcem.py:131)
       float* wdst = p.W + (size_t)b * F * K;
-      for (int i = tid; i < F * K; i += CT) { const int ff = i / K, k = i - ff * K; wdst[i] = W_s[ff * KS + k] / cn_s[k]; }
+      for (int i = tid; i < F * K; i += CCT) { const int ff = i / K, k = i - ff * K; wdst[i] = W_s[ff * KS + k] / cn_s[k]; }
     }
 
     // ---------------- pass A: H update with Vb = Wun @ H_old (mcem.py:113-121), chasing the copies
@@ -341,8 +363,8 @@ __global__ void __launch_bounds__(CT, 1) k_cols_v1(ColsArgs p) {
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) num[k] = den[k] = 0.f;
     for (int j = 0; j < NCH; ++j) {
-      mbar_wait(bars + j, par);
-      const int i0 = j * NI / NCH, i1 = (j + 1) * NI / NCH;
+      mbar_wait(full + j, par);
+      const int i0 = cb[j], i1 = cb[j + 1];
       const float* vs = data + (size_t)(i0 * 32 + fl) * NB + n;
       const float* wrow = W_s + (i0 * 32 + fl) * KS;
       for (int i = i0; i < i1; ++i, vs += 32 * NB, wrow += 32 * KS) {
@@ -387,31 +409,33 @@ __global__ void __launch_bounds__(CT, 1) k_cols_v1(ColsArgs p) {
         red[(warp * 2 * KMAX + KMAX + k) * NB + lane] = den[k];
       }
     }
-    __syncthreads();
+    bar_compute();
     if (tid < 2 * KMAX * NB) {
       float s = 0.f;
 #pragma unroll
       for (int w8 = 0; w8 < 8; ++w8) s += red[w8 * 2 * KMAX * NB + tid];
       red2[tid] = s;
     }
-    __syncthreads();
+    bar_compute();
     if (tid < KMAX * NB) {
       const int k = tid >> 3;
       Hn_s[tid] = (k < K) ? meta[tid] * sqrtf(red2[tid] / red2[KMAX * NB + tid]) : 0.f;
     }
-    __syncthreads();
+    bar_compute();
     float hn[KMAX];
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) hn[k] = Hn_s[k * NB + n];
+    if (RT > 0) {                                           // column data is in registers: release it to the producer
+      __syncwarp();
+      if (lane == 0) mbar_arrive(mempty);
+    }
 
     // ---------------- pass B: Vb = Wun @ H_new (kept for the next E-step, mcem.py:124); g update (:138-142)
     float ng = 0.f, dg = 0.f;
     {
       const float* vs = data + (size_t)fl * NB + n;
       const float* wrow = W_s + fl * KS;
-      const size_t o0 = (size_t)fl * NP + (size_t)t * NB + n;
-      float* vbo = p.Vb + o0;
-      uint32_t* xvo = p.XV != nullptr ? p.XV + o0 : nullptr;
+      float* vbo = p.Vb + (size_t)fl * NP + (size_t)t * NB + n;
       for (int i = 0; i < NI; ++i, vs += 32 * NB, wrow += 32 * KS, vbo += (size_t)32 * NP) {
         if (i * 32 + fl < F) {
           float vb = 0.f;
@@ -450,29 +474,28 @@ __global__ void __launch_bounds__(CT, 1) k_cols_v1(ColsArgs p) {
           dg += t1;
         }
       }
-      (void)xvo;
     }
     ng += __shfl_xor_sync(0xffffffffu, ng, 8);
     ng += __shfl_xor_sync(0xffffffffu, ng, 16);
     dg += __shfl_xor_sync(0xffffffffu, dg, 8);
     dg += __shfl_xor_sync(0xffffffffu, dg, 16);
     if (lane < NB) { red[(warp * 2) * NB + lane] = ng; red[(warp * 2 + 1) * NB + lane] = dg; }
-    __syncthreads();
+    bar_compute();
     float sn = 0.f, sd = 0.f;
 #pragma unroll
     for (int w8 = 0; w8 < 8; ++w8) { sn += red[(w8 * 2) * NB + n]; sd += red[(w8 * 2 + 1) * NB + n]; }
     const float gnew = gg * sqrtf(sn / sd);
-    // outputs of the tile (registers hold everything still needed from `meta`)
+    // outputs of the tile
     if (tid < NB && valid) p.g[(size_t)t * NB + n] = gnew;
     if (tid < KMAX * NB) {
       const int k = tid >> 3;
       if (k < K && valid) p.H[(size_t)k * NP + (size_t)t * NB + n] = Hn_s[tid] * cn_s[k];   // mcem.py:133
     }
 
-    // ---------------- pass C: cost with the new g (mcem.py:151-152, :68-70); refill behind it
+    // ---------------- pass C: cost with the new g (mcem.py:151-152, :68-70); chunks are released behind it
     float cl = 0.f, cr = 0.f;
     for (int j = 0; j < NCH; ++j) {
-      const int i0 = j * NI / NCH, i1 = (j + 1) * NI / NCH;
+      const int i0 = cb[j], i1 = cb[j + 1];
       const float* vs = data + (size_t)(i0 * 32 + fl) * NB + n;
       const float* wrow = W_s + (i0 * 32 + fl) * KS;
       for (int i = i0; i < i1; ++i, vs += 32 * NB, wrow += 32 * KS) {
@@ -508,41 +531,41 @@ __global__ void __launch_bounds__(CT, 1) k_cols_v1(ColsArgs p) {
           cr = fmaf(vs[R * PS], sr, cr);
         }
       }
-      __syncthreads();                                      // chunk j is free (and `red` of pass B is consumed)
-      if (has_next) {
-        if (warp == 0) { fence_proxy_async(); issue_chunk(t - 1, j); }
-        if (j == 0) issue_meta(t - 1);
-      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty + j);                // this warp is done with chunk j of this tile
+    }
+    if (RT == 0) {                                          // runtime-R path kept reading the column data until here
+      __syncwarp();
+      if (lane == 0) mbar_arrive(mempty);
     }
     float cs = valid ? fmaf(cl, 0.6931471805599453f, cr) : 0.f;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) cs += __shfl_xor_sync(0xffffffffu, cs, o);
     if (lane == 0) misc[warp] = cs;
-    __syncthreads();
+    bar_compute();
     if (tid == 0) {
       float s = 0.f;
       for (int w8 = 0; w8 < 8; ++w8) s += misc[w8];
       p.cost_part[t] = s;
     }
   }
-  cp_wait_dyn(0);
 }
 
 template <int KMAX, int RT>
 int32_t launch_cols(const ColsArgs& a, size_t smem, int grid, cudaStream_t st) {
   cudaError_t e = cudaFuncSetAttribute(k_cols_v1<KMAX, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return fail(GVN_E_CUDA, "k_cols_v1 smem attr (%zu B): %s", smem, cudaGetErrorString(e));
-  k_cols_v1<KMAX, RT><<<grid, CT, smem, st>>>(a);
+  k_cols_v1<KMAX, RT><<<grid, CTT, smem, st>>>(a);
   return check_launch("k_cols_v1");
 }
 
 template <int KMAX, int RT>
-int32_t launch_w(const gvn_batch* b, int R, cudaStream_t st) {
+int32_t launch_w(const gvn_batch* b, int R, const float* Mt, cudaStream_t st) {
   const size_t smem = (size_t)WS * w_stage_floats(b->K, R) * 4;
   cudaError_t e = cudaFuncSetAttribute(k_w_v2<KMAX, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return fail(GVN_E_CUDA, "k_w_v2 smem attr (%zu B): %s", smem, cudaGetErrorString(e));
   dim3 gw((b->F + WROWS - 1) / WROWS, b->B);
-  k_w_v2<KMAX, RT><<<gw, WT, smem, st>>>(b->F, b->K, b->NP, R, b->frame_off, b->n_frames, b->X2t, b->Vs, b->Vs_w, b->g, b->H, b->W, b->Wun);
+  k_w_v2<KMAX, RT><<<gw, WT, smem, st>>>(b->F, b->K, b->NP, R, b->frame_off, b->n_frames, b->X2t, b->Vs, Mt, b->W, b->Wun);
   return check_launch("k_w_v2");
 }
 
@@ -551,7 +574,7 @@ inline int ks_of(int K) { int ks = kmax_of(K); return (ks % 16 == 0) ? ks + 4 : 
 
 template <int KMAX>
 int32_t launch_v1_k(const gvn_batch* b, int R, const ColsArgs& a, size_t smem, int grid, cudaStream_t st) {
-  int32_t rc = R == 10 ? launch_w<KMAX, 10>(b, R, st) : launch_w<KMAX, 0>(b, R, st);
+  int32_t rc = R == 10 ? launch_w<KMAX, 10>(b, R, a.Mt, st) : launch_w<KMAX, 0>(b, R, a.Mt, st);
   if (rc) return rc;
   return R == 10 ? launch_cols<KMAX, 10>(a, smem, grid, st) : launch_cols<KMAX, 0>(a, smem, grid, st);
 }
@@ -561,21 +584,27 @@ int32_t launch_v1_k(const gvn_batch* b, int R, const ColsArgs& a, size_t smem, i
 // true when variant 1 can run this shape (the tile block must fit in shared memory)
 bool mstep_v1_supported(const gvn_batch* b, int R) {
   if (b->K > 16 || b->X2t == nullptr) return false;
-  const size_t bytes = cols_smem_floats(b->F, ks_of(b->K), R, kmax_of(b->K)) * 4;
+  const size_t bytes = cols_smem_floats(b->F, ks_of(b->K), b->K, R, kmax_of(b->K)) * 4;
   const size_t wbytes = (size_t)WS * w_stage_floats(b->K, R) * 4;
   return bytes <= 227 * 1024 && wbytes <= 227 * 1024;
 }
 
-int32_t launch_mstep_v1(const gvn_batch* b, int R, float* cost_part, cudaStream_t st) {
+// workspace of variant 1: the column data in tile order
+size_t mstep_v1_workspace_bytes(const gvn_batch* b) { return (size_t)(b->K + 1 + b->R_cap) * b->NP * sizeof(float); }
+
+int32_t launch_mstep_v1(const gvn_batch* b, int R, float* cost_part, float* Mt, cudaStream_t st) {
   const int KMAX = kmax_of(b->K);
+  k_tile_meta<<<148, 256, 0, st>>>(b->K, R, b->NP, b->H, b->g, b->Vs_w, Mt);
+  int32_t rc = check_launch("k_tile_meta");
+  if (rc) return rc;
   ColsArgs a;
   a.F = b->F; a.K = b->K; a.KS = ks_of(b->K); a.NP = b->NP; a.R = R; a.B = b->B;
   a.ntiles = b->NP / NB;
   const int NI = (b->F + 31) / 32;
   a.nchunk = NI < MAXCH ? NI : MAXCH;
-  a.frame_utt = b->frame_utt; a.frame_off = b->frame_off; a.X2t = b->X2t; a.Vs = b->Vs; a.Vs_w = b->Vs_w;
-  a.Vb = b->Vb; a.g = b->g; a.H = b->H; a.Wun = b->Wun; a.W = b->W; a.cost_part = cost_part; a.XV = nullptr;
-  const size_t smem = cols_smem_floats(b->F, a.KS, R, KMAX) * 4;
+  a.frame_utt = b->frame_utt; a.frame_off = b->frame_off; a.X2t = b->X2t; a.Vs = b->Vs; a.Mt = Mt;
+  a.Vb = b->Vb; a.g = b->g; a.H = b->H; a.Wun = b->Wun; a.W = b->W; a.cost_part = cost_part;
+  const size_t smem = cols_smem_floats(b->F, a.KS, b->K, R, KMAX) * 4;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
