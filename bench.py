@@ -210,7 +210,8 @@ def main():
     def host_step(seed=0):
         up = enh.upload(wavs, labels)
         s_hat, n_hat, cost, b = device_step(up, seed=seed)
-        out = (s_hat.cpu(), n_hat.cpu(), cost[-1].cpu())      # D2H of the results (synchronises)
+        out = (E.download(s_hat, "s_hat"), E.download(n_hat, "n_hat"), E.download(cost[-1].contiguous(), "cost"))
+        torch.cuda.current_stream().synchronize()             # D2H of the results into pinned host buffers
         return up["h2d_bytes"], s_hat.numel() * 4 + n_hat.numel() * 4 + cost.shape[1] * 8, out
 
     def barrier():

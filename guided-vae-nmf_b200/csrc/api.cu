@@ -38,6 +38,7 @@ size_t istft_workspace_bytes(const gvn_batch*, int);
 int32_t launch_istft(const gvn_batch*, const float*, int, int, const int32_t*, float*, int, void*, cudaStream_t);
 int32_t launch_dense(const float*, const float*, const float*, int, const float*, int, const float*, const float*, float,
                      int, int, int, float*, cudaStream_t);
+void set_profile_buffer(void*);
 int32_t launch_selftest_umma(const float*, const float*, int, int, int, float*, cudaStream_t);
 int32_t launch_pack_decoder(const float*, const float*, const float*, const float*, const float*, const float*, int, int,
                             int, void*, cudaStream_t);
@@ -161,6 +162,8 @@ int32_t gvn_dense(const float* W, const float* b, const float* in0, int32_t D0, 
   GVN_REQUIRE(act >= 0 && act <= 4, GVN_E_INVALID, "act=%d", act);
   return launch_dense(W, b, in0, D0, in1, D1, mean, std_, eps, D_out, NP, act, out, (cudaStream_t)stream);
 }
+
+void gvn_debug_profile_buffer(void* dev_u64) { set_profile_buffer(dev_u64); }
 
 int32_t gvn_selftest_umma(const float* A, const float* W, int32_t N, int32_t K, int32_t variant, float* D, void* stream) {
   GVN_REQUIRE(A && W && D, GVN_E_INVALID, "NULL pointer");

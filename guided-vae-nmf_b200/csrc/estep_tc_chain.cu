@@ -29,6 +29,8 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include <stdlib.h>
+
 #include <type_traits>
 
 #include "gvn_common.cuh"
@@ -48,13 +50,19 @@ constexpr int NTHREADS = 320;
 constexpr int SROWS = 32;               // frequency rows per TMA box
 constexpr int STAGE_BYTES = SROWS * TM * 4;
 constexpr int MAX_STAGES = 8;
+#ifndef GVN_TC_DEFAULT_VARIANT
+#define GVN_TC_DEFAULT_VARIANT 1
+#endif
 constexpr float W_SCALE_INV = 1.0f / 256.0f;
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
 constexpr float SC3 = W_SCALE_INV * LOG2E;
 
 // TMEM column map (512 columns allocated)
-constexpr uint32_t COL_ACC0 = 0, COL_ACC1 = 128, COL_ACCH = 256, COL_A = 384, COL_Z = 448;
+// The hidden-layer accumulator aliases output buffer 0 (the two are never live together), which
+// leaves columns 256..383 for the per-frame bias of the first layer (label projection + b1, fp32).
+constexpr uint32_t COL_ACC0 = 0, COL_ACC1 = 128, COL_ACCH = 0, COL_YP = 256, COL_A = 384, COL_Z = 448;
+constexpr uint32_t COL_LOGU = 464, COL_EPS = 480;     // L16 == 16 only: noise of the next step, double-buffered (see PRE)
 
 struct TcArgs {
   int F, FN, L, NP, burnin, R, nstage;
@@ -67,12 +75,31 @@ struct TcArgs {
   const float* b2;
   const float* eps; const float* u; const uint8_t* forced; uint64_t seed, chain;
   float* t_acc; uint8_t* t_dec; int32_t* t_cnt; float* t_zs;
+  unsigned long long* prof;            // optional [grid][10 warps][16] cycle counters (gvn_debug_profile_buffer)
 };
 
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float tanh_approx(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// 2^t on the FMA/ALU pipes (Cody-Waite split + degree-6 minimax, ~1e-7 relative): takes MUFU.EX2
+// work off the special-function pipe, which bounds the chain epilogue
+__device__ __forceinline__ float ex2_poly(float t) {
+  t = fmaxf(t, -125.f);
+  const float j = t + 12582912.f;                        // 1.5 * 2^23: round(t) lands in the low mantissa bits
+  const float f = t - (j - 12582912.f);                  // in [-0.5, 0.5]
+  float q = 1.535336188319500e-4f;
+  q = fmaf(q, f, 1.339887440266574e-3f);
+  q = fmaf(q, f, 9.618437357674640e-3f);
+  q = fmaf(q, f, 5.550332471162809e-2f);
+  q = fmaf(q, f, 2.402264791363012e-1f);
+  q = fmaf(q, f, 6.931472028550421e-1f);
+  q = fmaf(q, f, 1.0f);
+  return __int_as_float(__float_as_int(q) + (__float_as_int(j) << 23));
+}
+
+__device__ __forceinline__ void st_stream(float* p, float v) { asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
 
 __device__ __forceinline__ void bar_epilogue() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
@@ -91,7 +118,21 @@ __global__ void __launch_bounds__(256) k_pack_xv(size_t n4, const float4* __rest
   }
 }
 
-template <int L16>
+// parity wait for the two single-lane service warps: suspends in hardware between polls so that
+// their spinning does not take issue slots from the epilogue warps of the same scheduler
+__device__ __forceinline__ void mbar_wait_idle(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  for (uint32_t spins = 0; !ok; ++spins) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(20000u) : "memory");
+    if (spins > (1u << 16)) __trap();         // ~1 s: a protocol bug must fail fast
+  }
+}
+
+template <int L16, bool PROF_ON, int VAR>
 __global__ void __launch_bounds__(NTHREADS, 1) k_estep_tc(const __grid_constant__ CUtensorMap tm_xv, TcArgs p) {
   constexpr int K1 = 2 * L16;                             // z hi | z lo against [W1 | W1]
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -153,26 +194,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_estep_tc(const __grid_constant_
   if (warp == 9) {
     // =============================== TMA producer ===============================
     if (lane == 0) {
-      uint32_t it = 0;
+      uint32_t slot = 0, ph = 0;
       const int n_load_passes = 1 + n_steps;
       for (int ps = 0; ps < n_load_passes; ++ps) {
-        for (int s = 0; s < NST; ++s, ++it) {
-          const uint32_t slot = it % p.nstage, par = ((it / p.nstage) & 1) ^ 1;
-          mbar_wait(bar_empty + slot, par);
+        for (int s = 0; s < NST; ++s) {
+          mbar_wait_idle(bar_empty + slot, ph ^ 1);
           mbar_expect_tx(bar_full + slot, STAGE_BYTES);
           tma_load_2d(sRing + (size_t)slot * STAGE_BYTES, &tm_xv, n0, s * SROWS, bar_full + slot);
+          if (++slot == (uint32_t)p.nstage) { slot = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 8) {
     // =============================== MMA issuer ===============================
     if (lane == 0) {
-      uint32_t n_z = 0, n_h = 0, n_free[2] = {0, 0};
+      uint32_t n_z = 0, n_h = 0, n_free0 = 0, n_free1 = 0;
       const uint32_t sbo1 = img_sbo(K1), sbo = img_sbo(HID), lbo = img_lbo();
       const int n_pass = 1 + n_steps + (p.R > 0 ? 1 : 0);
       for (int ps = 0; ps < n_pass; ++ps) {
         // layer 1: ACCH = [z_hi | z_lo](128 x K1) * [W1 | W1]^T
-        mbar_wait(bar_z, n_z++ & 1);
+        mbar_wait_idle(bar_z, n_z++ & 1);
         fence_after();
 #pragma unroll
         for (int k0 = 0; k0 < K1; k0 += 16)
@@ -180,7 +221,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_estep_tc(const __grid_constant_
                  idesc_f16(TM, HID), k0 > 0);
         mma_commit(bar_hfull);
         // layer 2: ACCH = H1(128 x 128) * W2^T
-        mbar_wait(bar_h, n_h++ & 1);
+        mbar_wait_idle(bar_h, n_h++ & 1);
         fence_after();
 #pragma unroll
         for (int k0 = 0; k0 < HID; k0 += 16)
@@ -188,11 +229,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_estep_tc(const __grid_constant_
                  idesc_f16(TM, HID), k0 > 0);
         mma_commit(bar_hfull);
         // layer 3: chunks of the output features, alternating accumulator buffers
-        mbar_wait(bar_h, n_h++ & 1);
+        mbar_wait_idle(bar_h, n_h++ & 1);
         fence_after();
         for (int c = 0; c < NCH; ++c) {
           const int buf = c & 1, ncol = min(128, FN - c * 128);
-          mbar_wait(bar_free + buf, (n_free[buf]++ & 1) ^ 1);
+          if (buf) mbar_wait_idle(bar_free + 1, (n_free1++ & 1) ^ 1); else mbar_wait_idle(bar_free + 0, (n_free0++ & 1) ^ 1);
           fence_after();
           const uint32_t b0 = smem_u32(sW3) + (uint32_t)(c * 16) * sbo;
           const uint32_t idesc = idesc_f16(TM, ncol);
@@ -212,12 +253,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_estep_tc(const __grid_constant_
     const bool in_range = n < NP;
     const bool valid = in_range && p.frame_utt[n] >= 0;
     const float g = valid ? p.g[n] : 1.f;
-    uint32_t n_d[2] = {0, 0}, n_hf = 0, it = 0, n_dec = 0;
-    float z[L16], zp[L16];
-    uint32_t yp[32];                                      // label projection + b1 of this thread's 64 hidden units (f16 pairs)
+    uint32_t n_d0 = 0, n_d1 = 0, n_hf = 0, n_dec = 0;
+    uint32_t slot = 0, ph = 0;                            // ring position of the next stage
+    unsigned long long pc[PROF_ON ? 12 : 1] = {0}, pt = PROF_ON ? clock64() : 0ull;
+#define PROF(i) do { if constexpr (PROF_ON) { const unsigned long long t_ = clock64(); pc[i] += t_ - pt; pt = t_; } } while (0)
+    constexpr bool PRE = (L16 == 16);
+    float z[L16];
+    float zp[PRE ? 1 : L16];                              // without the TMEM noise hand-over the proposal is kept
+    // label projection + b1 of this thread's 64 hidden units -> TMEM (constant for the whole chain)
 #pragma unroll
-    for (int i = 0; i < 32; ++i)
-      yp[i] = in_range ? pack_f16(p.yproj[(size_t)(64 * half + 2 * i) * NP + n], p.yproj[(size_t)(64 * half + 2 * i + 1) * NP + n]) : 0u;
+    for (int c0 = 0; c0 < 64; c0 += 16) {
+      uint32_t w[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) w[i] = in_range ? __float_as_uint(p.yproj[(size_t)(64 * half + c0 + i) * NP + n]) : 0u;
+      tmem_st16(tlane + COL_YP + 64 * half + c0, w);
+    }
+    tmem_st_wait();
     double Ct = 0.0;
     int n_acc = 0;
     if (half == 0) {
@@ -225,6 +276,52 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_estep_tc(const __grid_constant_
       for (int l = 0; l < L16; ++l) z[l] = (l < L && in_range) ? p.Z[(size_t)l * NP + n] : 0.f;
       if (valid) for (int s = 0; s < p.R; ++s) p.Vs_w[(size_t)s * NP + n] = 0.f;
     }
+
+    // Noise of a step does not depend on the chain state.  With L16 == 16 there is room in TMEM to
+    // take it off the critical path: warps 4-7, which idle while the owners build a proposal, draw
+    // eps and log u of step m+1 at the start of step m and hand them over through TMEM columns
+    // (double-buffered on the step parity; ordered by the energy barrier that ends every step).
+    auto draw_eps = [&](int m, float (&e)[L16]) {
+      if (p.eps != nullptr) {
+#pragma unroll
+        for (int l = 0; l < L16; ++l) e[l] = (l < L && in_range) ? p.eps[((size_t)m * L + l) * NP + n] : 0.f;
+      } else {
+#pragma unroll
+        for (int lq = 0; lq < L16 / 4; ++lq) {
+          uint4 rr = philox4x32_10(make_uint4((uint32_t)n, (uint32_t)m, (uint32_t)lq, (uint32_t)p.chain),
+                                   make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32)));
+          float2 a = box_muller(rr.x, rr.y), b = box_muller(rr.z, rr.w);
+          const float e4[4] = {a.x, a.y, b.x, b.y};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) e[4 * lq + i] = (4 * lq + i < L) ? e4[i] : 0.f;
+        }
+      }
+    };
+    auto draw_logu = [&](int m) -> float {
+      float uu = 0.5f;
+      if (valid) {
+        if (p.u != nullptr) {
+          uu = p.u[(size_t)m * NP + n];
+        } else {
+          uint4 rr = philox4x32_10(make_uint4((uint32_t)n, (uint32_t)m, 0xffffffffu, (uint32_t)p.chain),
+                                   make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32)));
+          uu = u01(rr.x);
+        }
+      }
+      return logf(uu);
+    };
+    auto stage_noise = [&](int m) {                   // warps 4-7 (PRE): noise of step m -> TMEM
+      float e[L16];
+      draw_eps(m, e);
+      uint32_t w[16];
+#pragma unroll
+      for (int l = 0; l < 16; ++l) w[l] = __float_as_uint(e[l % L16]);
+      __syncwarp();
+      tmem_st16(tlane + COL_EPS + 16 * (m & 1), w);
+      tmem_st1(tlane + COL_LOGU + (m & 1), __float_as_uint(draw_logu(m)));
+      tmem_st_wait();
+      fence_before();
+    };
 
     auto put_z = [&](const float (&zz)[L16]) {       // warps 0-3: Z operand (hi | lo) -> TMEM, signal the issuer
 #pragma unroll
@@ -248,39 +345,36 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_estep_tc(const __grid_constant_
 
     // hidden layer epilogue: tanh(acc/256 + bias) of this thread's 64 columns -> f16 A operand in TMEM
     auto hidden = [&](auto layer0) {
+      PROF(0);
       mbar_wait(bar_hfull, n_hf++ & 1);
+      PROF(decltype(layer0)::value ? 1 : 3);
       fence_after();
 #pragma unroll
-      for (int c0 = 0; c0 < 64; c0 += 32) {
-        uint32_t r0[16], r1[16];
-        tmem_ld16(tlane + COL_ACCH + 64 * half + c0, r0);
-        tmem_ld16(tlane + COL_ACCH + 64 * half + c0 + 16, r1);
+      for (int c0 = 0; c0 < 64; c0 += 16) {
+        uint32_t r[16], bq[16];
+        tmem_ld16(tlane + COL_ACCH + 64 * half + c0, r);
+        if constexpr (decltype(layer0)::value) tmem_ld16(tlane + COL_YP + 64 * half + c0, bq);
         tmem_ld_wait();
-        uint32_t o0[8], o1[8];
+        uint32_t o[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          float b00, b01, b10, b11;
+          float b0, b1;
           if constexpr (decltype(layer0)::value) {
-            const float2 t0 = __half22float2(*reinterpret_cast<const __half2*>(&yp[c0 / 2 + j]));
-            const float2 t1 = __half22float2(*reinterpret_cast<const __half2*>(&yp[c0 / 2 + 8 + j]));
-            b00 = t0.x; b01 = t0.y; b10 = t1.x; b11 = t1.y;
+            b0 = __uint_as_float(bq[2 * j]); b1 = __uint_as_float(bq[2 * j + 1]);
           } else {
-            const float2 t0 = *reinterpret_cast<const float2*>(sB2 + 64 * half + c0 + 2 * j);
-            const float2 t1 = *reinterpret_cast<const float2*>(sB2 + 64 * half + c0 + 16 + 2 * j);
-            b00 = t0.x; b01 = t0.y; b10 = t1.x; b11 = t1.y;
+            const float2 t = *reinterpret_cast<const float2*>(sB2 + 64 * half + c0 + 2 * j);
+            b0 = t.x; b1 = t.y;
           }
-          o0[j] = pack_f16(tanh_approx(fmaf(__uint_as_float(r0[2 * j]), W_SCALE_INV, b00)),
-                           tanh_approx(fmaf(__uint_as_float(r0[2 * j + 1]), W_SCALE_INV, b01)));
-          o1[j] = pack_f16(tanh_approx(fmaf(__uint_as_float(r1[2 * j]), W_SCALE_INV, b10)),
-                           tanh_approx(fmaf(__uint_as_float(r1[2 * j + 1]), W_SCALE_INV, b11)));
+          o[j] = pack_f16(tanh_approx(fmaf(__uint_as_float(r[2 * j]), W_SCALE_INV, b0)),
+                          tanh_approx(fmaf(__uint_as_float(r[2 * j + 1]), W_SCALE_INV, b1)));
         }
-        tmem_st8(tlane + COL_A + (64 * half + c0) / 2, o0);
-        tmem_st8(tlane + COL_A + (64 * half + c0 + 16) / 2, o1);
+        tmem_st8(tlane + COL_A + (64 * half + c0) / 2, o);
       }
       tmem_st_wait();
       fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_h);
+      PROF(decltype(layer0)::value ? 2 : 4);
     };
 
     // one decoder evaluation.  ENERGY: stream X2/Vb and return sum_f log Vx + X2/Vx of the row
@@ -289,83 +383,105 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_estep_tc(const __grid_constant_
       constexpr bool ENERGY = decltype(energy_t)::value, STORE = decltype(store_t)::value;
       hidden(std::true_type{});
       hidden(std::false_type{});
-      double dl = 0.0, dr = 0.0;
+      double dsum = 0.0;
       float* vo = STORE ? vs_out + tile_off(16 * half, n, F) : nullptr;   // column-tile order: bin stride = 8 floats
 #pragma unroll 1
       for (int c = 0; c < NCH; ++c) {
         const int buf = c & 1, ncol = min(128, FN - c * 128);
-        mbar_wait(bar_d + buf, n_d[buf]++ & 1);
+        if (buf) mbar_wait(bar_d + 1, n_d1++ & 1); else mbar_wait(bar_d + 0, n_d0++ & 1);
+        PROF(5);
         fence_after();
         const uint32_t acc_col = (buf ? COL_ACC1 : COL_ACC0) + 16 * half;
         const int nst = (ncol + SROWS - 1) / SROWS;
-#pragma unroll 1
-        for (int s = 0; s < nst; ++s) {
-          const int f0 = c * 128 + s * SROWS + 16 * half;
-          uint32_t r[16];
-          tmem_ld16(tlane + acc_col + s * SROWS, r);
+        float sl = 0.f, sr = 0.f;                          // fp32 inside a chunk (<= 64 pairs), double across chunks
+        // one stage = this thread's 16 bins of a 32-row ring box; the accumulator columns of stage s+1
+        // are requested from TMEM before the math of stage s (two register sets, statically indexed)
+        constexpr bool V_PF = (VAR & 1) != 0;             // prefetch the next stage's accumulator columns
+        constexpr bool V_PRE = (VAR & 2) != 0;            // all shared-memory loads of a stage before its math
+        constexpr bool V_POLY = (VAR & 4) != 0;           // every second exp on the FMA pipe
+        auto stage = [&](uint32_t (&r)[16], uint32_t (&rn)[16], int s_) {
+          const int f0 = c * 128 + s_ * SROWS + 16 * half;
           const uint32_t* xv = nullptr;
-          uint32_t slot = 0;
+          if (!V_PF) tmem_ld16(tlane + acc_col + s_ * SROWS, r);
           if (ENERGY) {
-            slot = it % p.nstage;
-            mbar_wait(bar_full + slot, (it / p.nstage) & 1);
-            ++it;
+            PROF(7);
+            mbar_wait(bar_full + slot, ph);
+            PROF(6);
             xv = reinterpret_cast<const uint32_t*>(sRing + (size_t)slot * STAGE_BYTES) + (16 * half) * TM + row;
           }
-          float b3v[16];
-#pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            const float4 t = *reinterpret_cast<const float4*>(sB3 + f0 + 4 * j4);
-            b3v[4 * j4] = t.x; b3v[4 * j4 + 1] = t.y; b3v[4 * j4 + 2] = t.z; b3v[4 * j4 + 3] = t.w;
-          }
-          tmem_ld_wait();
-          float sl = 0.f, sr = 0.f;
+          if (V_PF && s_ + 1 < nst) tmem_ld16(tlane + acc_col + (s_ + 1) * SROWS, rn);   // prefetch
+          float* vo = STORE ? vs_out + tile_off(f0, n, F) : nullptr;              // column-tile order: bin stride = 8 floats
           if (f0 + 16 <= F) {                              // full group: 8 pairs of bins
+            float b3v[16];
+            uint32_t wv[16];
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const float4 t = *reinterpret_cast<const float4*>(sB3 + f0 + 4 * j4);
+              b3v[4 * j4] = t.x; b3v[4 * j4 + 1] = t.y; b3v[4 * j4 + 2] = t.z; b3v[4 * j4 + 3] = t.w;
+            }
+            if (ENERGY && V_PRE) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) wv[j] = xv[j * TM];
+              asm volatile("" ::: "memory");
+            }
+            if (!V_PF) tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const float v0 = ex2_approx(fmaf(__uint_as_float(r[2 * j]), SC3, b3v[2 * j]));
-              const float v1 = ex2_approx(fmaf(__uint_as_float(r[2 * j + 1]), SC3, b3v[2 * j + 1]));
+              const float t0 = fmaf(__uint_as_float(r[2 * j]), SC3, b3v[2 * j]), t1 = fmaf(__uint_as_float(r[2 * j + 1]), SC3, b3v[2 * j + 1]);
+              const float v0 = ex2_approx(t0);
+              const float v1 = V_POLY ? ex2_poly(t1) : ex2_approx(t1);
               if (ENERGY) {
-                const uint32_t w0 = xv[(2 * j) * TM], w1 = xv[(2 * j + 1) * TM];
+                const uint32_t w0 = V_PRE ? wv[2 * j] : xv[(2 * j) * TM], w1 = V_PRE ? wv[2 * j + 1] : xv[(2 * j + 1) * TM];
                 const float a = fmaf(g, v0, __uint_as_float(w0 << 16)), b = fmaf(g, v1, __uint_as_float(w1 << 16));
                 const float pr = a * b;
                 sl += lg2_approx(pr);
                 const float qn = fmaf(__uint_as_float(w0 & 0xffff0000u), b, __uint_as_float(w1 & 0xffff0000u) * a);
                 sr = fmaf(qn, rcp_approx(pr), sr);
               }
-              if (STORE && valid) { vo[(2 * j) * 8] = v0; vo[(2 * j + 1) * 8] = v1; }
+              if (STORE && valid) { st_stream(vo + (2 * j) * 8, v0); st_stream(vo + (2 * j + 1) * 8, v1); }
             }
           } else {                                         // ragged tail of the spectrum (F = 513: one bin)
             const int nv = F - f0;
+            if (!V_PF) tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               if (j >= nv) break;
-              const float v0 = ex2_approx(fmaf(__uint_as_float(r[j]), SC3, b3v[j]));
+              const float v0 = ex2_approx(fmaf(__uint_as_float(r[j]), SC3, sB3[f0 + j]));
               if (ENERGY) {
                 const uint32_t w0 = xv[j * TM];
                 const float a = fmaf(g, v0, __uint_as_float(w0 << 16));
                 sl += lg2_approx(a);
                 sr = fmaf(__uint_as_float(w0 & 0xffff0000u), rcp_approx(a), sr);
               }
-              if (STORE && valid) vo[j * 8] = v0;
+              if (STORE && valid) st_stream(vo + j * 8, v0);
             }
           }
-          if (STORE) vo += SROWS * 8;
           if (ENERGY) {
-            dl += (double)sl;
-            dr += (double)sr;
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_empty + slot);
+            if (++slot == (uint32_t)p.nstage) { slot = 0; ph ^= 1; }
           }
+          if (V_PF) tmem_ld_wait();                        // the prefetched columns are in registers
+        };
+        uint32_t ra[16], rb[16];
+        if (V_PF) { tmem_ld16(tlane + acc_col, ra); tmem_ld_wait(); }
+#pragma unroll 1
+        for (int s = 0; s < nst; s += 2) {
+          stage(ra, rb, s);
+          if (s + 1 < nst) stage(V_PF ? rb : ra, ra, s + 1);
         }
+        if (ENERGY) dsum += (double)fmaf(sl, LN2, sr);
         fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_free + buf);
+        PROF(7);
       }
       if (!ENERGY) return 0.0;
       double* part = sPart + (n_dec & 1) * NE;
       ++n_dec;
-      part[tid] = fma(dl, (double)LN2, dr);
+      part[tid] = dsum;
       bar_epilogue();
+      PROF(8);
       return part[row] + part[row + 128];
     };
     const std::true_type T{};
@@ -373,37 +489,42 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_estep_tc(const __grid_constant_
 
     // ---- chain ----
     if (half == 0) put_z(z);
+    if (PRE && half == 1 && n_steps > 0) stage_noise(0);
     Ct = decode(T, N, nullptr);
     int cur = 0;
     float cnt = 0.f;
 
 #pragma unroll 1
     for (int m = 0; m < n_steps; ++m) {
-      float prior = 0.f;
+      float prior = 0.f, logu = 0.f;
       if (half == 0) {
         // proposal Z' = Z + sd * eps  (mcem.py:257)
-        if (p.eps != nullptr) {
+        float e[L16];
+        if (PRE) {
+          uint32_t w[16];
+          fence_after();
+          __syncwarp();
+          tmem_ld16(tlane + COL_EPS + 16 * (m & 1), w);
+          logu = __uint_as_float(tmem_ld1(tlane + COL_LOGU + (m & 1)));
+          tmem_ld_wait();
 #pragma unroll
-          for (int l = 0; l < L16; ++l) {
-            float e = (l < L && in_range) ? p.eps[((size_t)m * L + l) * NP + n] : 0.f;
-            zp[l] = z[l] + p.sd * e;
-          }
+          for (int l = 0; l < L16; ++l) e[l] = __uint_as_float(w[l % 16]);
         } else {
-#pragma unroll
-          for (int lq = 0; lq < L16 / 4; ++lq) {
-            uint4 rr = philox4x32_10(make_uint4((uint32_t)n, (uint32_t)m, (uint32_t)lq, (uint32_t)p.chain),
-                                     make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32)));
-            float2 a = box_muller(rr.x, rr.y), b = box_muller(rr.z, rr.w);
-            float e[4] = {a.x, a.y, b.x, b.y};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) { const int l = 4 * lq + i; zp[l] = (l < L) ? z[l] + p.sd * e[i] : 0.f; }
-          }
+          draw_eps(m, e);
         }
+        float zq[L16];
 #pragma unroll
-        for (int l = 0; l < L16; ++l) prior += z[l] * z[l] - zp[l] * zp[l];
-        put_z(zp);
+        for (int l = 0; l < L16; ++l) { zq[l] = fmaf(p.sd, e[l], z[l]); prior += z[l] * z[l] - zq[l] * zq[l]; }
+        if (!PRE) {
+#pragma unroll
+          for (int l = 0; l < L16; ++l) zp[l % (PRE ? 1 : L16)] = zq[l];
+        }
+        put_z(zq);
+      } else if (PRE && m + 1 < n_steps) {
+        stage_noise(m + 1);
       }
       const int r = m - p.burnin;
+      PROF(9);
       const double Cp = (r >= 1) ? decode(T, T, p.Vs + (size_t)r * F * NP) : decode(T, N, nullptr);
 
       // accept / reject (mcem.py:266-280)
@@ -411,24 +532,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_estep_tc(const __grid_constant_
         const float acc_prob = (float)(Ct - Cp) + 0.5f * prior;
         int ok = 0;
         if (valid) {
-          float uu;
-          if (p.u != nullptr) {
-            uu = p.u[(size_t)m * NP + n];
-          } else {
-            uint4 rr = philox4x32_10(make_uint4((uint32_t)n, (uint32_t)m, 0xffffffffu, (uint32_t)p.chain),
-                                     make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32)));
-            uu = u01(rr.x);
-          }
-          ok = logf(uu) < acc_prob;
+          if (!PRE) logu = draw_logu(m);
+          ok = logu < acc_prob;
           if (p.forced != nullptr) ok = p.forced[(size_t)m * NP + n] != 0;
           if (p.t_acc != nullptr) p.t_acc[(size_t)m * NP + n] = acc_prob;
           if (p.t_dec != nullptr) p.t_dec[(size_t)m * NP + n] = (uint8_t)ok;
         }
-        if (ok) {
-          Ct = Cp; ++n_acc;
+        if (PRE) {                                          // z += sd * eps with the same noise, re-read from TMEM
+          uint32_t w[16];                                   // (aligned TMEM load: executed by the whole warp)
+          __syncwarp();
+          tmem_ld16(tlane + COL_EPS + 16 * (m & 1), w);
+          tmem_ld_wait();
+          if (ok) {
 #pragma unroll
-          for (int l = 0; l < L16; ++l) z[l] = zp[l];
+            for (int l = 0; l < L16; ++l) z[l] = fmaf(p.sd, __uint_as_float(w[l % 16]), z[l]);
+          }
+        } else if (ok) {
+#pragma unroll
+          for (int l = 0; l < L16; ++l) z[l] = zp[l % (PRE ? 1 : L16)];
         }
+        if (ok) { Ct = Cp; ++n_acc; }
         if (r >= 0 && p.t_zs != nullptr && valid) {
 #pragma unroll
           for (int l = 0; l < L16; ++l) if (l < L) p.t_zs[((size_t)r * L + l) * NP + n] = z[l];
@@ -445,6 +568,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_estep_tc(const __grid_constant_
         if (half == 0) put_z(z);
         decode(N, T, p.Vs);
       }
+    }
+    PROF(9);
+    if constexpr (PROF_ON) {
+      if (p.prof != nullptr && lane == 0)
+        for (int i = 0; i < 12; ++i) p.prof[((size_t)blockIdx.x * 10 + warp) * 16 + i] = pc[i];
     }
     if (half == 0 && valid) {
 #pragma unroll
@@ -491,7 +619,7 @@ int32_t make_tile_map(CUtensorMap* m, const uint32_t* base, int F, int NP) {
   return GVN_OK;
 }
 
-template <int L16>
+template <int L16, bool PROF_ON, int VAR>
 int32_t launch_tc(const CUtensorMap& mx, const TcArgs& a, int grid, cudaStream_t st) {
   const size_t fixed = (size_t)HID * 2 * L16 * 2 + (size_t)HID * HID * 2 + (size_t)a.FN * HID * 2 + (size_t)(a.FN + 16 + HID) * 4 +
                        (size_t)2 * NE * 8 + (7 + 2 * MAX_STAGES) * 8 + 16;
@@ -502,13 +630,20 @@ int32_t launch_tc(const CUtensorMap& mx, const TcArgs& a, int grid, cudaStream_t
   if (nstage < 2) return fail(GVN_E_UNSUPPORTED_SHAPE, "tensor-core E-step: shared memory does not fit (F=%d L=%d)", a.F, a.L);
   args.nstage = nstage;
   const size_t smem = fixed + (size_t)nstage * STAGE_BYTES;
-  cudaError_t e = cudaFuncSetAttribute(k_estep_tc<L16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return fail(GVN_E_CUDA, "estep_tc smem attr (%zu B): %s", smem, cudaGetErrorString(e));
-  k_estep_tc<L16><<<grid, NTHREADS, smem, st>>>(mx, args);
+  static size_t smem_set = 0;                           // the attribute is sticky: set it once per size
+  if (smem_set != smem) {
+    cudaError_t e = cudaFuncSetAttribute(k_estep_tc<L16, PROF_ON, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(GVN_E_CUDA, "estep_tc smem attr (%zu B): %s", smem, cudaGetErrorString(e));
+    smem_set = smem;
+  }
+  k_estep_tc<L16, PROF_ON, VAR><<<grid, NTHREADS, smem, st>>>(mx, args);
   return check_launch("k_estep_tc");
 }
 
 }  // namespace
+
+static unsigned long long* g_prof = nullptr;
+void set_profile_buffer(void* p) { g_prof = reinterpret_cast<unsigned long long*>(p); }
 
 int32_t launch_estep_tc(const gvn_batch* b, const void* packed, int burnin, int R, float var_RW, const gvn_noise* nz,
                         const gvn_trace* tr, int precision, cudaStream_t st) {
@@ -524,8 +659,13 @@ int32_t launch_estep_tc(const gvn_batch* b, const void* packed, int burnin, int 
                                      reinterpret_cast<uint4*>(b->XV));
   int32_t rc = check_launch("k_pack_xv");
   if (rc) return rc;
-  CUtensorMap mx;
-  if ((rc = make_tile_map(&mx, b->XV, b->F, b->NP))) return rc;
+  static thread_local CUtensorMap mx;                   // encoded once per (pointer, shape)
+  static thread_local const void* mx_ptr = nullptr;
+  static thread_local int mx_F = 0, mx_NP = 0;
+  if (mx_ptr != b->XV || mx_F != b->F || mx_NP != b->NP) {
+    if ((rc = make_tile_map(&mx, b->XV, b->F, b->NP))) return rc;
+    mx_ptr = b->XV; mx_F = b->F; mx_NP = b->NP;
+  }
   TcArgs a;
   a.F = b->F; a.FN = t.FN; a.L = b->L; a.NP = b->NP; a.burnin = burnin; a.R = R; a.nstage = 0;
   a.sd = sqrtf(var_RW);
@@ -535,9 +675,24 @@ int32_t launch_estep_tc(const gvn_batch* b, const void* packed, int burnin, int 
   a.eps = nz->eps; a.u = nz->u; a.forced = nz->forced_accept; a.seed = nz->seed; a.chain = nz->chain;
   a.t_acc = tr ? tr->acc_prob : nullptr; a.t_dec = tr ? tr->accepted : nullptr;
   a.t_cnt = tr ? tr->n_accepted : nullptr; a.t_zs = tr ? tr->z_samples : nullptr;
+  a.prof = g_prof;
   const int grid = (b->NP + TM - 1) / TM;
-  if (t.L16 == 16) return launch_tc<16>(mx, a, grid, st);
-  if (t.L16 == 32) return launch_tc<32>(mx, a, grid, st);
+  static int var = -1;                                  // GVN_TC_VARIANT: epilogue scheduling experiments (see `stage`)
+  if (var < 0) { const char* e = getenv("GVN_TC_VARIANT"); var = e ? atoi(e) & 7 : GVN_TC_DEFAULT_VARIANT; }
+  if (t.L16 == 16) {
+    if (a.prof != nullptr) return launch_tc<16, true, GVN_TC_DEFAULT_VARIANT>(mx, a, grid, st);
+    switch (var) {
+      case 0: return launch_tc<16, false, 0>(mx, a, grid, st);
+      case 1: return launch_tc<16, false, 1>(mx, a, grid, st);
+      case 2: return launch_tc<16, false, 2>(mx, a, grid, st);
+      case 3: return launch_tc<16, false, 3>(mx, a, grid, st);
+      case 4: return launch_tc<16, false, 4>(mx, a, grid, st);
+      case 5: return launch_tc<16, false, 5>(mx, a, grid, st);
+      case 6: return launch_tc<16, false, 6>(mx, a, grid, st);
+      default: return launch_tc<16, false, 7>(mx, a, grid, st);
+    }
+  }
+  if (t.L16 == 32) return launch_tc<32, false, GVN_TC_DEFAULT_VARIANT>(mx, a, grid, st);
   return fail(GVN_E_UNSUPPORTED_SHAPE, "tensor-core E-step supports L <= 32 (got %d)", b->L);
 }
 

@@ -84,7 +84,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok) : "r"(s_u32(bar)), "r"(parity) : "memory");
-    if (spins > (1u << 26)) __trap();       // a protocol bug must surface as an error, not a hang
+    if (spins > (1u << 22)) __trap();       // a protocol bug must surface as an error, not a hang
   }
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -553,8 +553,12 @@ __global__ void __launch_bounds__(CTT, 1) k_cols_v1(ColsArgs p) {
 
 template <int KMAX, int RT>
 int32_t launch_cols(const ColsArgs& a, size_t smem, int grid, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(k_cols_v1<KMAX, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return fail(GVN_E_CUDA, "k_cols_v1 smem attr (%zu B): %s", smem, cudaGetErrorString(e));
+  static size_t smem_set = 0;
+  if (smem_set != smem) {
+    cudaError_t e = cudaFuncSetAttribute(k_cols_v1<KMAX, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(GVN_E_CUDA, "k_cols_v1 smem attr (%zu B): %s", smem, cudaGetErrorString(e));
+    smem_set = smem;
+  }
   k_cols_v1<KMAX, RT><<<grid, CTT, smem, st>>>(a);
   return check_launch("k_cols_v1");
 }
@@ -562,8 +566,12 @@ int32_t launch_cols(const ColsArgs& a, size_t smem, int grid, cudaStream_t st) {
 template <int KMAX, int RT>
 int32_t launch_w(const gvn_batch* b, int R, const float* Mt, cudaStream_t st) {
   const size_t smem = (size_t)WS * w_stage_floats(b->K, R) * 4;
-  cudaError_t e = cudaFuncSetAttribute(k_w_v2<KMAX, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return fail(GVN_E_CUDA, "k_w_v2 smem attr (%zu B): %s", smem, cudaGetErrorString(e));
+  static size_t smem_set = 0;
+  if (smem_set != smem) {
+    cudaError_t e = cudaFuncSetAttribute(k_w_v2<KMAX, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(GVN_E_CUDA, "k_w_v2 smem attr (%zu B): %s", smem, cudaGetErrorString(e));
+    smem_set = smem;
+  }
   dim3 gw((b->F + WROWS - 1) / WROWS, b->B);
   k_w_v2<KMAX, RT><<<gw, WT, smem, st>>>(b->F, b->K, b->NP, R, b->frame_off, b->n_frames, b->X2t, b->Vs, Mt, b->W, b->Wun);
   return check_launch("k_w_v2");
@@ -605,9 +613,12 @@ int32_t launch_mstep_v1(const gvn_batch* b, int R, float* cost_part, float* Mt, 
   a.frame_utt = b->frame_utt; a.frame_off = b->frame_off; a.X2t = b->X2t; a.Vs = b->Vs; a.Mt = Mt;
   a.Vb = b->Vb; a.g = b->g; a.H = b->H; a.Wun = b->Wun; a.W = b->W; a.cost_part = cost_part;
   const size_t smem = cols_smem_floats(b->F, a.KS, b->K, R, KMAX) * 4;
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
   const int grid = a.ntiles < sms ? a.ntiles : sms;
   switch (KMAX) {
     case 4: return launch_v1_k<4>(b, R, a, smem, grid, st);

@@ -140,6 +140,8 @@ class Batch:
         self._struct = None
 
     def struct(self):
+        if self._struct is not None:            # pointers and dims never change after construction
+            return C.byref(self._struct)
         s = GvnBatch()
         s.B, s.F, s.K, s.L, s.NP, s.R_cap = self.B, self.F, self.K, self.L, self.NP, self.R_cap
         for name in ("frame_off", "n_frames", "frame_utt", "X2", "Xc", "W", "Wun", "H", "g", "Vb", "Z", "Vs", "yproj", "Vs_w", "XV", "X2t"):
@@ -193,16 +195,38 @@ def stft_geometry(T, fs, wlen_sec, hop_percent):
     return nfft, hop, end_pad, 1 + Tx // hop
 
 
+_PINNED = {}
+
+
+def pinned_buffer(tag, shape, dtype=torch.float32):
+    """Page-locked staging buffer, allocated once per (tag, shape) and reused: cudaHostAlloc of tens of
+    megabytes per call costs more than the copy it serves."""
+    key = (tag, tuple(shape), dtype)
+    buf = _PINNED.get(key)
+    if buf is None:
+        buf = torch.zeros(*shape, dtype=dtype).pin_memory()
+        _PINNED[key] = buf
+    return buf
+
+
 def upload_waveforms(wavs, device, pinned=None):
     """Packs B waveforms into one zero-padded (B, T_stride) f32 tensor on the device."""
     B = len(wavs)
     T = [len(w) for w in wavs]
     T_stride = (max(T) + 3) // 4 * 4
-    host = pinned if pinned is not None else torch.zeros(B, T_stride, dtype=torch.float32).pin_memory()
+    host = pinned if pinned is not None else pinned_buffer("wav", (B, T_stride))
+    hn = host.numpy()
     for b, w in enumerate(wavs):
-        host[b, :T[b]] = torch.as_tensor(np.asarray(w, dtype=np.float32))
-        host[b, T[b]:] = 0
+        hn[b, :T[b]] = np.asarray(w, dtype=np.float32)
+        hn[b, T[b]:] = 0
     return host.to(device, non_blocking=True), T, T_stride
+
+
+def download(t, tag):
+    """Device tensor -> reused pinned host buffer (asynchronous on the current stream)."""
+    host = pinned_buffer(tag, t.shape, t.dtype)
+    host.copy_(t, non_blocking=True)
+    return host
 
 
 def stft_into(batch, wav_dev, T, T_stride, n_fft, hop, end_pad):

@@ -195,6 +195,10 @@ int32_t gvn_init_nmf(const gvn_batch* batch /*HOST*/, const float* rand_W /*[B][
 int32_t gvn_selftest_umma(const float* A, const float* W, int32_t N, int32_t K, int32_t variant,
                           float* D, void* stream);
 
+/* Debug: when set to a device buffer of [n_tiles][18][16] u64, the tensor-core chain kernel writes
+ * per-warp cycle counters of its phases (tools/estep_phases.py); NULL switches it off. */
+void gvn_debug_profile_buffer(void* dev_u64);
+
 #ifdef __cplusplus
 }
 #endif

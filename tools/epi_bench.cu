@@ -1,0 +1,72 @@
+// Microbenchmark of the chain epilogue's inner loop in isolation (no barriers, no TMEM, no TMA):
+// per pair of bins 2 FFMA + 2 EX2 + 2 LDS + unpack + 2 FFMA + FMUL + LG2 + RCP + 2 FFMA, data in shared
+// memory.  Reports cycles per 16-bin group per warp with W warps per scheduler.
+#include <cstdio>
+#include <cuda_runtime.h>
+__device__ __forceinline__ float ex2a(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2a(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcpa(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+template <int MODE>
+__global__ void k(float* out, long long* cyc, int iters) {
+  __shared__ unsigned xv[32 * 128];
+  __shared__ float b3[32];
+  for (int i = threadIdx.x; i < 32 * 128; i += blockDim.x) xv[i] = 0x3f803f80u;
+  if (threadIdx.x < 32) b3[threadIdx.x] = 0.01f * threadIdx.x;
+  __syncthreads();
+  const int row = threadIdx.x & 127, half = (threadIdx.x >> 7) & 1;
+  float r[16];
+  for (int i = 0; i < 16; ++i) r[i] = 1.0f + threadIdx.x * 1e-3f + i;
+  float sl = 0.f, sr = 0.f;
+  const float g = 1.1f;
+  long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+    const unsigned* x = xv + 16 * half * 128 + row;
+    unsigned wv[16];
+    float bv[16];
+    if (MODE == 3) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const uint4 t = *reinterpret_cast<const uint4*>(xv + row * 32 + (((4 * half + c) ^ (row & 7)) << 2));
+        wv[4 * c] = t.x; wv[4 * c + 1] = t.y; wv[4 * c + 2] = t.z; wv[4 * c + 3] = t.w;
+        const float4 u = *reinterpret_cast<const float4*>(b3 + 16 * half + 4 * c);
+        bv[4 * c] = u.x; bv[4 * c + 1] = u.y; bv[4 * c + 2] = u.z; bv[4 * c + 3] = u.w;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float2 bb;
+      if (MODE == 3) { bb.x = bv[2 * j]; bb.y = bv[2 * j + 1]; } else bb = *reinterpret_cast<const float2*>(b3 + 16 * half + 2 * j);
+      float v0, v1;
+      if (MODE == 2) { v0 = fmaf(r[2 * j], 0.0056f, bb.x); v1 = fmaf(r[2 * j + 1], 0.0056f, bb.y); }   // no exp
+      else { v0 = ex2a(fmaf(r[2 * j], 0.0056f, bb.x)); v1 = ex2a(fmaf(r[2 * j + 1], 0.0056f, bb.y)); }
+      const unsigned w0 = MODE == 3 ? wv[2 * j] : x[(2 * j) * 128], w1 = MODE == 3 ? wv[2 * j + 1] : x[(2 * j + 1) * 128];
+      const float a = fmaf(g, v0, __uint_as_float(w0 << 16)), b = fmaf(g, v1, __uint_as_float(w1 << 16));
+      const float pr = a * b;
+      if (MODE != 1) sl += lg2a(pr); else sl += pr;
+      const float qn = fmaf(__uint_as_float(w0 & 0xffff0000u), b, __uint_as_float(w1 & 0xffff0000u) * a);
+      if (MODE != 1) sr = fmaf(qn, rcpa(pr), sr); else sr = fmaf(qn, pr, sr);
+    }
+    r[it & 15] += sl * 1e-30f;      // loop-carried, keeps everything live
+  }
+  long long t1 = clock64();
+  out[blockIdx.x * blockDim.x + threadIdx.x] = sl + sr;
+  if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
+template <int MODE>
+void run(const char* name, int threads) {
+  float* out; long long* cyc;
+  cudaMalloc(&out, 148 * 1024 * 4); cudaMalloc(&cyc, 148 * 8);
+  const int iters = 4000;
+  k<MODE><<<148, threads>>>(out, cyc, iters);
+  k<MODE><<<148, threads>>>(out, cyc, iters);
+  cudaDeviceSynchronize();
+  long long h[148]; cudaMemcpy(h, cyc, 148 * 8, cudaMemcpyDeviceToHost);
+  double c = 0; for (int i = 0; i < 148; ++i) c += h[i]; c /= 148;
+  printf("%-28s %4d threads (%d warps/scheduler): %.0f cycles per 16-bin group per scheduler (MUFU floor %d)\n", name, threads, threads / 128,
+         c / iters, (MODE == 0 || MODE == 3) ? 32 * 8 * (threads / 128) : (MODE == 1 ? 16 * 8 * (threads / 128) : 16 * 8 * (threads / 128)));
+  cudaFree(out); cudaFree(cyc);
+}
+int main() {
+  for (int th : {128, 256, 512}) { run<0>("full (ex2+lg2+rcp)", th); run<3>("full, LDS.128 swizzled", th); run<1>("ex2 only", th); run<2>("lg2+rcp only", th); }
+  return 0;
+}

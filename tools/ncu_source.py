@@ -26,11 +26,13 @@ for r in rows[hi + 1:]:
     op = op.split(".")[0]
     ops[op] += n; samp_ops[op] += s
     tot_inst += n; tot_samp += s
-    lines.append((s, n, r[ix["Address"]], sass))
+    st = {h[6:]: int(r[i] or 0) for h, i in ix.items() if h.startswith("stall_") and "Not Issued" not in h and r[i].isdigit()}
+    top_st = ",".join("%s:%d" % kv for kv in sorted(st.items(), key=lambda x: -x[1])[:3] if kv[1] > 0)
+    lines.append((s, n, r[ix["Address"]], sass + "   | " + top_st))
 print("total warp instructions %d, samples %d" % (tot_inst, tot_samp))
 print("--- by opcode (instructions | samples)")
 for op, n in ops.most_common(25):
     print("  %-12s %6.2f%%  %6.2f%%" % (op, 100.0 * n / tot_inst, 100.0 * samp_ops[op] / max(1, tot_samp)))
 print("--- hottest SASS instructions by stall samples")
 for s, n, a, sass in sorted(lines, reverse=True)[:top]:
-    print("  %6.2f%% samp %6.2f%% inst  %s  %s" % (100.0 * s / max(1, tot_samp), 100.0 * n / tot_inst, a[-5:], sass[:110]))
+    print("  %6.2f%% samp %6.2f%% inst  %s  %s" % (100.0 * s / max(1, tot_samp), 100.0 * n / tot_inst, a[-5:], sass[:150]))
