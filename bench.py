@@ -165,7 +165,9 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--niter", type=int, default=100)
     ap.add_argument("--rank-k", type=int, default=10)
-    ap.add_argument("--precision", default=os.environ.get("GVN_PRECISION", "fp32"))
+    ap.add_argument("--precision", default=os.environ.get("GVN_PRECISION", "f16"),
+                    help="decoder arithmetic inside the chain: f16 = tcgen05 tensor cores, f16 operands (11-bit mantissa = "
+                         "TF32) with fp32 accumulate -- the north star's tensor-core mode; fp32 = CUDA-core parity mode")
     ap.add_argument("--mstep-variant", type=int, default=int(os.environ.get("GVN_MSTEP_VARIANT", "1")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -223,9 +225,12 @@ def main():
     up = enh.upload(wavs, labels)
     for i in range(args.warmup):
         device_step(up, seed=i)
+    from gvn import _lib
+    lib = _lib.load()
     timers = E.KernelTimers()
     clocks = ClockSampler(local)
     barrier()
+    launches0 = int(lib.gvn_launch_count())
     if rank == 0:
         clocks.start()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -234,6 +239,7 @@ def main():
         s_hat, n_hat, cost, b = device_step(up, timers=timers, seed=100 + i)
     t1.record()
     barrier()
+    launches = int(lib.gvn_launch_count()) - launches0      # kernels of libgvn.so launched inside the timed region
     clk = clocks.stop() if rank == 0 else None
     ms = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -275,7 +281,12 @@ def main():
     m_ms_tot = timers.total_ms("mstep")
     nmf_bytes = args.steps * args.niter * 2 * (R_E + 1) * b.F * frames * 4
     m_gbs = nmf_bytes / (m_ms_tot * 1e-3) / 1e9
-    launches_per_step = 2 + 1 + 5 + (args.niter + 1) + 3 * args.niter + 1 + 1 + 4   # stft, init x2, dense x5, chains, mstep x3, cost, wiener, istft x2x2
+    # DRAM traffic per launch of the two hot kernels from the committed ncu --set full capture (profiles/)
+    traffic = {}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))
+    except Exception:
+        pass
     n_e = timers.count("estep")
 
     if rank == 0:
@@ -285,14 +296,14 @@ def main():
             "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "f16 operands, f32 accumulate",
             "data": "synthetic", "config": workload(args), "clocks": clk,
             "e2e": {"value": e2e_value, "unit": "utt/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
-            "gpu_launches": int(launches_per_step * args.steps),
+            "gpu_launches": launches,
             "roofline": {"kernel": "gvn_estep (decoder MLP + MH chain, %s)" % args.precision, "bound": "tensor",
                          "achieved": e_tflops, "peak": tf_peak, "unit": "TFLOP/s", "frac": e_tflops / tf_peak,
-                         "traffic": None, "peak_source": peak_src + " bf16_tflops_sustained",
+                         "traffic": traffic.get("estep_bytes_per_launch"), "peak_source": peak_src + " bf16_tflops_sustained",
                          "avg_launch_ms": e_ms_tot / n_e, "launches": n_e, "share_of_step": e_ms_tot / (ms_step * args.steps)},
-            "roofline_nmf": {"kernel": "gvn_mstep (k_mstep_w + k_colnorm + k_mstep_cols)", "bound": "hbm",
+            "roofline_nmf": {"kernel": "gvn_mstep (k_tile_meta + k_w_v2 + k_cols_v1)", "bound": "hbm",
                              "achieved": m_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": m_gbs / hbm_peak,
-                             "traffic": None, "peak_source": peak_src + " hbm_gbs",
+                             "traffic": traffic.get("mstep_bytes_per_launch"), "peak_source": peak_src + " hbm_gbs",
                              "avg_launch_ms": m_ms_tot / timers.count("mstep"),
                              "share_of_step": m_ms_tot / (ms_step * args.steps)},
         }

@@ -19,7 +19,10 @@ int32_t fail(int32_t code, const char* fmt, ...) {
   return code;
 }
 
+static unsigned long long g_launches = 0;      // kernels launched by this library (one check_launch per launch)
+
 int32_t check_launch(const char* what) {
+  ++g_launches;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(GVN_E_CUDA, "%s: CUDA error %d (%s)", what, (int)e, cudaGetErrorString(e));
   return GVN_OK;
@@ -164,6 +167,7 @@ int32_t gvn_dense(const float* W, const float* b, const float* in0, int32_t D0, 
 }
 
 void gvn_debug_profile_buffer(void* dev_u64) { set_profile_buffer(dev_u64); }
+uint64_t gvn_launch_count(void) { return g_launches; }
 
 int32_t gvn_selftest_umma(const float* A, const float* W, int32_t N, int32_t K, int32_t variant, float* D, void* stream) {
   GVN_REQUIRE(A && W && D, GVN_E_INVALID, "NULL pointer");

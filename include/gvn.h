@@ -199,6 +199,9 @@ int32_t gvn_selftest_umma(const float* A, const float* W, int32_t N, int32_t K, 
  * per-warp cycle counters of its phases (tools/estep_phases.py); NULL switches it off. */
 void gvn_debug_profile_buffer(void* dev_u64);
 
+/* Number of kernels this library has launched in the calling process so far. */
+uint64_t gvn_launch_count(void);
+
 #ifdef __cplusplus
 }
 #endif
