@@ -69,6 +69,39 @@ __device__ __forceinline__ void single_acc(float g, float vb, float va, float wa
   s2 = fmaf(ta, ia, s2);
 }
 
+// ---- packed fp32x2 arithmetic (FFMA2 / FMUL2 / FADD2 of sm_100): the column sweep is bound by the
+// FMA pipe, where a 3-register FFMA sustains ~0.6 warp-instructions per clock and scheduler
+// (register-bank limit, tools/ffma2_bench.cu) while FFMA2 carries two per instruction at ~0.45
+typedef float2 f2;
+__device__ __forceinline__ f2 F2(float x, float y) { return make_float2(x, y); }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ f2 rcp2(f2 a) { return make_float2(rcp_fast(a.x), rcp_fast(a.y)); }
+__device__ __forceinline__ f2 lg2_2(f2 a) { return make_float2(lg2_fast(a.x), lg2_fast(a.y)); }
+
+// four slots at once: slots (r0, r1) play `a`, slots (r2, r3) play `c` of two independent pairs
+__device__ __forceinline__ void quad_acc(f2 g2, f2 vb2, f2 va, f2 vc, f2 wa, f2 wc, f2& s1, f2& s2) {
+  const f2 a = fma2(g2, va, vb2), c = fma2(g2, vc, vb2);
+  const f2 ip = rcp2(mul2(a, c));
+  const f2 t1 = mul2(wa, c), t2 = mul2(wc, a);            // w/a = w * c * 1/(ac)
+  s1 = fma2(add2(t1, t2), ip, s1);
+  s2 = fma2(fma2(t1, c, mul2(t2, a)), mul2(ip, ip), s2);
+}
+__device__ __forceinline__ void quad_accB(f2 g2, f2 vb2, f2 va, f2 vc, f2 wa, f2 wc, f2& t1, f2& t2) {
+  const f2 a = fma2(g2, va, vb2), c = fma2(g2, vc, vb2);
+  const f2 ip = rcp2(mul2(a, c));
+  const f2 ia = mul2(c, ip), ic = mul2(a, ip);
+  const f2 ua = mul2(mul2(wa, va), ia), uc = mul2(mul2(wc, vc), ic);
+  t1 = add2(t1, add2(ua, uc));
+  t2 = fma2(ua, ia, fma2(uc, ic, t2));
+}
+__device__ __forceinline__ void quad_accC(f2 g2, f2 vb2, f2 va, f2 vc, f2 wa, f2 wc, f2& sl, f2& sr) {
+  const f2 a = fma2(g2, va, vb2), c = fma2(g2, vc, vb2);
+  sl = fma2(wa, lg2_2(a), fma2(wc, lg2_2(c), sl));
+  sr = fma2(fma2(wa, c, mul2(wc, a)), rcp2(mul2(a, c)), sr);
+}
+
 // ---- bulk async copies (TMA engine, no tensor map) + mbarrier -------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(bar)), "r"(count) : "memory");
@@ -230,17 +263,19 @@ struct ColsArgs {
   float* Vb; float* g; float* H; const float* Wun; float* W; float* cost_part;
 };
 
-constexpr int CCT = 256;              // compute threads of the column sweep
+constexpr int CCT = 384;              // compute threads of the column sweep: 12 warps (+1 producer) = at most 4 per scheduler
+constexpr int CFL = CCT / NB;         // frequency lanes (rows handled per thread-loop iteration)
+constexpr int CW = CCT / 32;          // compute warps
 constexpr int CTT = CCT + 32;         // + producer warp
 
 // shared memory (floats): data[(R+1)][F][NB] (plane R = X2) | W_s[F][KS] | red[8][2*KMAX][NB] |
 // red2[2*KMAX][NB] | Hn_s[KMAX][NB] | meta[K+1+R][NB] + fu[NB] | cn_s[KMAX] | misc[32] | bars
 __host__ __device__ inline size_t cols_smem_floats(int F, int KS, int K, int R, int KMAX) {
-  return (size_t)(R + 1) * F * NB + (size_t)F * KS + (size_t)8 * 2 * KMAX * NB + (size_t)2 * KMAX * NB + (size_t)KMAX * NB +
+  return (size_t)(R + 1) * F * NB + (size_t)F * KS + (size_t)CW * 2 * KMAX * NB + (size_t)2 * KMAX * NB + (size_t)KMAX * NB +
          (size_t)(K + 1 + R + 1) * NB + KMAX + 32 + 2 * (2 * MAXCH + 2) + 4 + 2 * (MAXCH + 1);
 }
 
-__device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, %0;" ::"n"(CCT) : "memory"); }
 
 template <int KMAX, int RT>
 __global__ void __launch_bounds__(CTT, 1) k_cols_v1(ColsArgs p) {
@@ -252,7 +287,7 @@ __global__ void __launch_bounds__(CTT, 1) k_cols_v1(ColsArgs p) {
   float* data = sm;
   float* W_s = data + (size_t)(R + 1) * PS;
   float* red = W_s + (size_t)F * KS;
-  float* red2 = red + 8 * 2 * KMAX * NB;
+  float* red2 = red + CW * 2 * KMAX * NB;
   float* Hn_s = red2 + 2 * KMAX * NB;
   float* meta = Hn_s + KMAX * NB;                           // H_old [K][NB] | g [NB] | Vs_w [R][NB]   (one bulk copy)
   float* cn_s = meta + (MR + 1) * NB;
@@ -265,7 +300,7 @@ __global__ void __launch_bounds__(CTT, 1) k_cols_v1(ColsArgs p) {
   int* cb = reinterpret_cast<int*>(bars + 2 * MAXCH + 2);   // [NCH+1] chunk boundaries in units of 32 rows
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int NI = (F + 31) / 32, NCH = p.nchunk, T8 = NP / NB;
+  const int NI = (F + CFL - 1) / CFL, NCH = p.nchunk, T8 = NP / NB;
 
   // contiguous tile range of this CTA, walked from the END of the batch: the W sweep that ran
   // just before leaves the tail of Vs in L2
@@ -295,7 +330,7 @@ __global__ void __launch_bounds__(CTT, 1) k_cols_v1(ColsArgs p) {
       }
       for (int j = 0; j < NCH; ++j) {
         if (it > 0) mbar_wait(empty + j, (it - 1) & 1);
-        const int r0 = cb[j] * 32, r1 = min(cb[j + 1] * 32, F);
+        const int r0 = cb[j] * CFL, r1 = min(cb[j + 1] * CFL, F);
         const uint32_t bytes = (uint32_t)(r1 - r0) * NB * 4;
         if (lane == 0) mbar_expect_tx(full + j, bytes * (R + 1));
         __syncwarp();
@@ -309,7 +344,7 @@ __global__ void __launch_bounds__(CTT, 1) k_cols_v1(ColsArgs p) {
   }
 
   // ================= compute warps =================
-  const int n = tid & (NB - 1), fl = tid >> 3;              // column of the tile, frequency lane (0..31)
+  const int n = tid & (NB - 1), fl = tid >> 3;              // column of the tile, frequency lane
   int cur_b = -1, cur_fo = -1;
   uint32_t par = 0;                                         // phase parity of the barriers for this tile
   for (int t = t_hi - 1; t >= t_lo; --t, par ^= 1) {
@@ -365,23 +400,32 @@ __global__ void __launch_bounds__(CTT, 1) k_cols_v1(ColsArgs p) {
     for (int j = 0; j < NCH; ++j) {
       mbar_wait(full + j, par);
       const int i0 = cb[j], i1 = cb[j + 1];
-      const float* vs = data + (size_t)(i0 * 32 + fl) * NB + n;
-      const float* wrow = W_s + (i0 * 32 + fl) * KS;
-      for (int i = i0; i < i1; ++i, vs += 32 * NB, wrow += 32 * KS) {
-        if (i * 32 + fl < F) {
+      const float* vs = data + (size_t)(i0 * CFL + fl) * NB + n;
+      const float* wrow = W_s + (i0 * CFL + fl) * KS;
+      for (int i = i0; i < i1; ++i, vs += CFL * NB, wrow += CFL * KS) {
+        if (i * CFL + fl < F) {
           float w[KMAX];
 #pragma unroll
           for (int k4 = 0; k4 < KMAX; k4 += 4) {
             const float4 t4 = *reinterpret_cast<const float4*>(wrow + k4);
             w[k4] = t4.x; w[k4 + 1] = t4.y; w[k4 + 2] = t4.z; w[k4 + 3] = t4.w;
           }
-          float vb = 0.f;
+          f2 vbp = F2(0.f, 0.f);
 #pragma unroll
-          for (int k = 0; k < KMAX; ++k) vb = fmaf(w[k], hk[k], vb);
+          for (int k = 0; k < KMAX; k += 2) vbp = fma2(F2(w[k], w[k + 1]), F2(hk[k], hk[k + 1]), vbp);
+          const float vb = vbp.x + vbp.y;
           float s1 = 0.f, s2 = 0.f;
           if (RT > 0) {
+            f2 s1v = F2(0.f, 0.f), s2v = F2(0.f, 0.f);
+            const f2 g2 = F2(gg, gg), vb2 = F2(vb, vb);
 #pragma unroll
-            for (int r = 0; r + 1 < RT; r += 2) pair_acc(gg, vb, vs[r * PS], vs[(r + 1) * PS], wgt(r), wgt(r + 1), s1, s2);
+            for (int r = 0; r + 3 < RT; r += 4)
+              quad_acc(g2, vb2, F2(vs[r * PS], vs[(r + 1) * PS]), F2(vs[(r + 2) * PS], vs[(r + 3) * PS]), F2(wgt(r), wgt(r + 1)),
+                       F2(wgt(r + 2), wgt(r + 3)), s1v, s2v);
+            s1 = s1v.x + s1v.y;
+            s2 = s2v.x + s2v.y;
+            constexpr int R4 = RT / 4 * 4;
+            if (RT - R4 >= 2) pair_acc(gg, vb, vs[R4 * PS], vs[(R4 + 1) * PS], wgt(R4), wgt(R4 + 1), s1, s2);
             if (RT & 1) single_acc(gg, vb, vs[(RT - 1) * PS], wgt(RT - 1), s1, s2);
           } else {
             int r = 0;
@@ -389,12 +433,17 @@ __global__ void __launch_bounds__(CTT, 1) k_cols_v1(ColsArgs p) {
             if (r < R) single_acc(gg, vb, vs[r * PS], wgt(r), s1, s2);
           }
           const float a = vs[R * PS] * s2;
+          const f2 a2 = F2(a, a), d2 = F2(s1, s1);
 #pragma unroll
-          for (int k = 0; k < KMAX; ++k) { num[k] = fmaf(w[k], a, num[k]); den[k] = fmaf(w[k], s1, den[k]); }
+          for (int k = 0; k < KMAX; k += 2) {
+            const f2 w2 = F2(w[k], w[k + 1]);
+            const f2 nn = fma2(w2, a2, F2(num[k], num[k + 1])), dd = fma2(w2, d2, F2(den[k], den[k + 1]));
+            num[k] = nn.x; num[k + 1] = nn.y; den[k] = dd.x; den[k + 1] = dd.y;
+          }
         }
       }
     }
-    // reduce over the 32 frequency lanes: lanes (8,16) in the warp, then the 8 warps
+    // reduce over the frequency lanes: lanes (8,16) in the warp, then the warps
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) {
       num[k] += __shfl_xor_sync(0xffffffffu, num[k], 8);
@@ -413,7 +462,7 @@ __global__ void __launch_bounds__(CTT, 1) k_cols_v1(ColsArgs p) {
     if (tid < 2 * KMAX * NB) {
       float s = 0.f;
 #pragma unroll
-      for (int w8 = 0; w8 < 8; ++w8) s += red[w8 * 2 * KMAX * NB + tid];
+      for (int w8 = 0; w8 < CW; ++w8) s += red[w8 * 2 * KMAX * NB + tid];
       red2[tid] = s;
     }
     bar_compute();
@@ -436,16 +485,19 @@ __global__ void __launch_bounds__(CTT, 1) k_cols_v1(ColsArgs p) {
       const float* vs = data + (size_t)fl * NB + n;
       const float* wrow = W_s + fl * KS;
       float* vbo = p.Vb + (size_t)fl * NP + (size_t)t * NB + n;
-      for (int i = 0; i < NI; ++i, vs += 32 * NB, wrow += 32 * KS, vbo += (size_t)32 * NP) {
-        if (i * 32 + fl < F) {
-          float vb = 0.f;
+      for (int i = 0; i < NI; ++i, vs += CFL * NB, wrow += CFL * KS, vbo += (size_t)CFL * NP) {
+        if (i * CFL + fl < F) {
+          f2 vbp = F2(0.f, 0.f);
 #pragma unroll
           for (int k4 = 0; k4 < KMAX; k4 += 4) {
             const float4 t4 = *reinterpret_cast<const float4*>(wrow + k4);
-            vb = fmaf(t4.x, hn[k4], fmaf(t4.y, hn[k4 + 1], fmaf(t4.z, hn[k4 + 2], fmaf(t4.w, hn[k4 + 3], vb))));
+            vbp = fma2(F2(t4.x, t4.y), F2(hn[k4], hn[k4 + 1]), fma2(F2(t4.z, t4.w), F2(hn[k4 + 2], hn[k4 + 3]), vbp));
           }
+          const float vb = vbp.x + vbp.y;
           if (valid) *vbo = vb;
           float t1 = 0.f, t2 = 0.f;
+          f2 t1v = F2(0.f, 0.f), t2v = F2(0.f, 0.f);
+          const f2 g2 = F2(gg, gg), vb2 = F2(vb, vb);
           auto pairB = [&](float va, float vc, float wa, float wc) {
             const float a = fmaf(gg, va, vb), c = fmaf(gg, vc, vb);
             const float ip = rcp_fast(a * c);
@@ -463,7 +515,13 @@ __global__ void __launch_bounds__(CTT, 1) k_cols_v1(ColsArgs p) {
           };
           if (RT > 0) {
 #pragma unroll
-            for (int r = 0; r + 1 < RT; r += 2) pairB(vs[r * PS], vs[(r + 1) * PS], wgt(r), wgt(r + 1));
+            for (int r = 0; r + 3 < RT; r += 4)
+              quad_accB(g2, vb2, F2(vs[r * PS], vs[(r + 1) * PS]), F2(vs[(r + 2) * PS], vs[(r + 3) * PS]), F2(wgt(r), wgt(r + 1)),
+                        F2(wgt(r + 2), wgt(r + 3)), t1v, t2v);
+            t1 = t1v.x + t1v.y;
+            t2 = t2v.x + t2v.y;
+            constexpr int R4 = RT / 4 * 4;
+            if (RT - R4 >= 2) pairB(vs[R4 * PS], vs[(R4 + 1) * PS], wgt(R4), wgt(R4 + 1));
             if (RT & 1) singleB(vs[(RT - 1) * PS], wgt(RT - 1));
           } else {
             int r = 0;
@@ -483,7 +541,7 @@ __global__ void __launch_bounds__(CTT, 1) k_cols_v1(ColsArgs p) {
     bar_compute();
     float sn = 0.f, sd = 0.f;
 #pragma unroll
-    for (int w8 = 0; w8 < 8; ++w8) { sn += red[(w8 * 2) * NB + n]; sd += red[(w8 * 2 + 1) * NB + n]; }
+    for (int w8 = 0; w8 < CW; ++w8) { sn += red[(w8 * 2) * NB + n]; sd += red[(w8 * 2 + 1) * NB + n]; }
     const float gnew = gg * sqrtf(sn / sd);
     // outputs of the tile
     if (tid < NB && valid) p.g[(size_t)t * NB + n] = gnew;
@@ -496,17 +554,20 @@ __global__ void __launch_bounds__(CTT, 1) k_cols_v1(ColsArgs p) {
     float cl = 0.f, cr = 0.f;
     for (int j = 0; j < NCH; ++j) {
       const int i0 = cb[j], i1 = cb[j + 1];
-      const float* vs = data + (size_t)(i0 * 32 + fl) * NB + n;
-      const float* wrow = W_s + (i0 * 32 + fl) * KS;
-      for (int i = i0; i < i1; ++i, vs += 32 * NB, wrow += 32 * KS) {
-        if (i * 32 + fl < F) {
-          float vb = 0.f;
+      const float* vs = data + (size_t)(i0 * CFL + fl) * NB + n;
+      const float* wrow = W_s + (i0 * CFL + fl) * KS;
+      for (int i = i0; i < i1; ++i, vs += CFL * NB, wrow += CFL * KS) {
+        if (i * CFL + fl < F) {
+          f2 vbp = F2(0.f, 0.f);
 #pragma unroll
           for (int k4 = 0; k4 < KMAX; k4 += 4) {
             const float4 t4 = *reinterpret_cast<const float4*>(wrow + k4);
-            vb = fmaf(t4.x, hn[k4], fmaf(t4.y, hn[k4 + 1], fmaf(t4.z, hn[k4 + 2], fmaf(t4.w, hn[k4 + 3], vb))));
+            vbp = fma2(F2(t4.x, t4.y), F2(hn[k4], hn[k4 + 1]), fma2(F2(t4.z, t4.w), F2(hn[k4 + 2], hn[k4 + 3]), vbp));
           }
+          const float vb = vbp.x + vbp.y;
           float sl = 0.f, sr = 0.f;
+          f2 slv = F2(0.f, 0.f), srv = F2(0.f, 0.f);
+          const f2 g2 = F2(gnew, gnew), vb2 = F2(vb, vb);
           auto pairC = [&](float va, float vc, float wa, float wc) {
             const float a = fmaf(gnew, va, vb), c = fmaf(gnew, vc, vb);
             sl = fmaf(wa, lg2_fast(a), sl);
@@ -520,7 +581,13 @@ __global__ void __launch_bounds__(CTT, 1) k_cols_v1(ColsArgs p) {
           };
           if (RT > 0) {
 #pragma unroll
-            for (int r = 0; r + 1 < RT; r += 2) pairC(vs[r * PS], vs[(r + 1) * PS], wgt(r), wgt(r + 1));
+            for (int r = 0; r + 3 < RT; r += 4)
+              quad_accC(g2, vb2, F2(vs[r * PS], vs[(r + 1) * PS]), F2(vs[(r + 2) * PS], vs[(r + 3) * PS]), F2(wgt(r), wgt(r + 1)),
+                        F2(wgt(r + 2), wgt(r + 3)), slv, srv);
+            sl = slv.x + slv.y;
+            sr = srv.x + srv.y;
+            constexpr int R4 = RT / 4 * 4;
+            if (RT - R4 >= 2) pairC(vs[R4 * PS], vs[(R4 + 1) * PS], wgt(R4), wgt(R4 + 1));
             if (RT & 1) singleC(vs[(RT - 1) * PS], wgt(RT - 1));
           } else {
             int r = 0;
@@ -545,7 +612,7 @@ __global__ void __launch_bounds__(CTT, 1) k_cols_v1(ColsArgs p) {
     bar_compute();
     if (tid == 0) {
       float s = 0.f;
-      for (int w8 = 0; w8 < 8; ++w8) s += misc[w8];
+      for (int w8 = 0; w8 < CW; ++w8) s += misc[w8];
       p.cost_part[t] = s;
     }
   }
@@ -608,7 +675,7 @@ int32_t launch_mstep_v1(const gvn_batch* b, int R, float* cost_part, float* Mt, 
   ColsArgs a;
   a.F = b->F; a.K = b->K; a.KS = ks_of(b->K); a.NP = b->NP; a.R = R; a.B = b->B;
   a.ntiles = b->NP / NB;
-  const int NI = (b->F + 31) / 32;
+  const int NI = (b->F + CFL - 1) / CFL;
   a.nchunk = NI < MAXCH ? NI : MAXCH;
   a.frame_utt = b->frame_utt; a.frame_off = b->frame_off; a.X2t = b->X2t; a.Vs = b->Vs; a.Mt = Mt;
   a.Vb = b->Vb; a.g = b->g; a.H = b->H; a.Wun = b->Wun; a.W = b->W; a.cost_part = cost_part;
