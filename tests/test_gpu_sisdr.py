@@ -1,0 +1,92 @@
+"""End-to-end agreement of the enhanced signal (north star: SI-SDR within 0.05 dB): one synthetic
+4 s utterance at the benchmark shape (F=513, K=10, L=16, M2 with oracle IBM labels) enhanced by
+(a) the oracle = the reference's torch-CPU algorithm on a recorded noise tape, (b) the CUDA path in
+fp32 mode replaying the same tape, (c) the tensor-core (f16) mode replaying the same tape,
+(d) the tensor-core mode on its own Philox stream.  (a)-(b) is the parity claim; (c) and (d) differ
+from (a) by Monte-Carlo noise only (a near-tie decision that flips restarts an independent chain)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+KW = dict(fs=16000, wlen_sec=64e-3, win="hann", hop_percent=0.25)
+
+
+def _si_sdr(est, s, n):
+    from python.metrics import energy_ratios
+    return energy_ratios(est, s, n)[0]
+
+
+def test_si_sdr_agreement_with_the_oracle():
+    from gvn.synth import synth_utterance
+    from oracle import stft_oracle
+    from oracle.mcem_oracle import McemOracle, NoiseTape, split_state_dict
+    from python.models.mcem import MCEM_M2
+    from python.models.models import DeepGenerativeModel
+    from python.processing.stft import stft, istft
+    from python.processing.target import clean_speech_IBM
+
+    x, s, n = synth_utterance(0, seed=11, T=64000)
+    X = stft_oracle.stft(x, dtype="complex64", **KW)                        # (F, N)
+    y = torch.from_numpy(clean_speech_IBM(stft_oracle.stft(s, dtype="complex64", **KW), 0.999, 0.999).T.copy())
+    F, N, L, K, niter = X.shape[0], X.shape[1], 16, 10, 12
+    torch.manual_seed(0)
+    vae = DeepGenerativeModel([F, F, L, [128, 128]], None).eval()
+    chain = (10, 30, 25, 75)
+
+    # (a) oracle with a recorded tape
+    o = McemOracle(niter, *chain, 0.01, model="M2")
+    o.trace = []
+    tape = NoiseTape(seed=5)
+    sd = vae.state_dict()
+    o.init_parameters(X.T, y, split_state_dict(sd, "decoder"), split_state_dict(sd, "encoder"), K, 1e-8, tape)
+    o.run()
+    d = tape.draws
+    eps = np.stack([t.numpy() for k, t in d[2:] if k == "randn"])
+    u = np.stack([t.numpy() for k, t in d[2:] if k == "rand"])
+    s_o = stft_oracle.istft(o.S_hat, max_len=len(x), **KW)
+    sdr_o = _si_sdr(s_o, s, n)
+
+    def run_gpu(precision, replay):
+        m = MCEM_M2(niter, *chain, 0.01)
+        m.precision = precision
+        m.seed = 123
+        if replay:
+            m.replay = dict(rand_W=d[0][1], rand_H=d[1][1], eps=eps, u=u)
+        m.init_parameters(X=X.T, y=y.cuda(), vae=vae, nmf_rank=K, eps=1e-8, device="cuda:0")
+        m.run()
+        return _si_sdr(istft(m.S_hat, max_len=len(x), **KW), s, n)
+
+    sdr_fp32 = run_gpu("fp32", True)
+    sdr_tc = run_gpu("f16", True)
+    sdr_tc_philox = run_gpu("f16", False)
+    print("SI-SDR [dB]: oracle %.4f | fp32 replay %.4f | f16 replay %.4f | f16 philox %.4f" % (sdr_o, sdr_fp32, sdr_tc, sdr_tc_philox))
+    assert abs(sdr_fp32 - sdr_o) < 0.05                    # parity (same noise, same decisions up to ties)
+    assert abs(sdr_tc - sdr_o) < 0.05                      # measured 0.0001 dB (same tape) and 0.012 dB (own stream)
+    assert abs(sdr_tc_philox - sdr_o) < 0.05
+
+
+@pytest.mark.parametrize("precision", ["f16", "fp32"])
+def test_config4_shape_properties(precision):
+    """BASELINE config 4 (NMF stress): M1, 30 s utterance (N = 1876 frames), K = 32, 10 kept samples per
+    frame (MCEM_M1(burnin_E_step=10)).  Size-independent properties at the full shape."""
+    from gvn.synth import synth_utterance
+    from python.models.mcem import MCEM_M1
+    from python.models.models import VariationalAutoencoder
+    from python.processing.stft import stft
+    x, s, n = synth_utterance(1, seed=4, T=480000)
+    X = stft(x, dtype="complex64", **KW)
+    assert X.shape == (513, 1876)
+    torch.manual_seed(0)
+    vae = VariationalAutoencoder([513, 16, [128, 128]]).eval()
+    m = MCEM_M1(niter=3, nsamples_E_step=10, burnin_E_step=10, nsamples_WF=25, burnin_WF=12, var_RW=0.01)
+    m.precision = precision
+    m.seed = 7
+    m.init_parameters(X=X.T, vae=vae, nmf_rank=32, eps=1e-8, device="cuda:0")
+    cost = m.run()
+    assert np.all(np.isfinite(cost)) and cost[-1] < cost[0]
+    assert m.Vs.shape == (12, 513, 1876)                                   # Wiener chain keeps burnin_WF samples (quirk)
+    np.testing.assert_allclose(m.W.abs().sum(0).cpu().numpy(), 1.0, rtol=1e-5)
+    np.testing.assert_allclose(m.S_hat + m.N_hat, X, rtol=1e-4, atol=1e-6 * np.max(np.abs(X)))
+    assert m.S_hat.shape == (513, 1876) and m.S_hat.dtype == np.complex64
