@@ -65,8 +65,8 @@ def make_inputs(n, first, T=64000):
     from oracle import stft_oracle                       # input preparation only (labels)
     from python.processing.target import clean_speech_IBM
     x, s, nz = synth_batch(n, seed=0, T=T, first=first)
-    labels = [clean_speech_IBM(stft_oracle.stft(si, dtype="complex64", **STFT_KW), 0.999, 0.999) for si in s]
-    return x, s, nz, labels
+    labels = [clean_speech_IBM(stft_oracle.stft(si, dtype="complex64", **STFT_KW), 0.999, 0.999).astype(np.uint8) for si in s]
+    return x, s, nz, labels                                  # binary masks as bytes (0/1), waveforms float64
 
 
 def decoder_flops_per_frame(L=16, F=513):
@@ -194,27 +194,24 @@ def main():
     x, s, nz, labels = make_inputs(B, first=rank * B)       # this rank's shard of the utterance list
     wavs = list(x)
 
-    gather_buf = [torch.zeros(B, 2, dtype=torch.float64, device=dev) for _ in range(world)] if world > 1 else None
+    gather_buf = [torch.zeros(B, 5, dtype=torch.float64, device=dev) for _ in range(world)] if world > 1 else None
+    utt_ids = torch.arange(rank * B, rank * B + B, device=dev, dtype=torch.float64)
 
-    def finish_step(cost):
-        # per-utterance result rows [utt_id, final cost]; the only collective of the path
-        rows = torch.stack([torch.arange(rank * B, rank * B + B, device=dev, dtype=torch.float64), cost[-1]], 1)
+
+    def finish_step(s_hat, cost, refs, T):
+        # per-utterance result rows [utt_id, SI-SDR, SI-SIR, SI-SAR, final cost] (python/metrics.py:12-60 on the
+        # device); bringing them together is the only collective of the path
+        q = E.energy_ratios(s_hat[:, :refs[0].shape[1]].contiguous(), refs[0], refs[1], T)
+        rows = torch.cat([utt_ids[:, None], q, cost[-1][:, None]], 1)
         if world > 1:
             dist.all_gather(gather_buf, rows)
         return rows
 
-    def device_step(up, timers=None, seed=0):
+    def device_step(up, refs, timers=None, seed=0):
         b = enh.prepare(None, None, seed=seed, uploaded=up)
         s_hat, n_hat, cost = enh.run(b, seed=seed, timers=timers)
-        finish_step(cost)
-        return s_hat, n_hat, cost, b
-
-    def host_step(seed=0):
-        up = enh.upload(wavs, labels)
-        s_hat, n_hat, cost, b = device_step(up, seed=seed)
-        out = (E.download(s_hat, "s_hat"), E.download(n_hat, "n_hat"), E.download(cost[-1].contiguous(), "cost"))
-        torch.cuda.current_stream().synchronize()             # D2H of the results into pinned host buffers
-        return up["h2d_bytes"], s_hat.numel() * 4 + n_hat.numel() * 4 + cost.shape[1] * 8, out
+        rows = finish_step(s_hat, cost, refs, b.T)
+        return s_hat, n_hat, cost, b, rows
 
     def barrier():
         if world > 1:
@@ -222,9 +219,10 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident timing ---------------------------------------------------------
-    up = enh.upload(wavs, labels)
+    up = enh.upload(wavs, labels, refs=(s, nz), slot=2)
+    refs = (up["ref_s"], up["ref_n"])
     for i in range(args.warmup):
-        device_step(up, seed=i)
+        device_step(up, refs, seed=i)
     from gvn import _lib
     lib = _lib.load()
     timers = E.KernelTimers()
@@ -236,7 +234,7 @@ def main():
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
     for i in range(args.steps):
-        s_hat, n_hat, cost, b = device_step(up, timers=timers, seed=100 + i)
+        s_hat, n_hat, cost, b, rows = device_step(up, refs, timers=timers, seed=100 + i)
     t1.record()
     barrier()
     launches = int(lib.gvn_launch_count()) - launches0      # kernels of libgvn.so launched inside the timed region
@@ -249,19 +247,30 @@ def main():
     assert bool(torch.isfinite(cost).all()) and bool(torch.isfinite(s_hat).all()), "non-finite result"
 
     # ---- end-to-end timing (host buffers in, host buffers out) --------------------------
-    host_step()
+    # Enhancer.enhance_many is the public batched API: every step packs this step's waveforms, labels and
+    # metric references into pinned memory, copies them to the device, enhances, and reads both enhanced
+    # waveforms + the result rows back into pinned host memory; the upload of step i+1 overlaps step i.
+    def batches(k):
+        for _ in range(k):
+            yield dict(wavs=wavs, labels=labels, refs=(s, nz))
+    for out in enh.enhance_many(batches(2), seed=150):
+        pass
     barrier()
     w0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(args.steps):
-        h2d, d2h, out = host_step(seed=200 + i)
+    for out in enh.enhance_many(batches(args.steps), seed=200):
+        h2d, d2h = out["h2d_bytes"], out["d2h_bytes"]
+        if world > 1:                                        # the step's only collective: gather the result rows
+            rows_e = torch.cat([utt_ids[:, None], out["metrics"].to(dev), out["cost"][-1].to(dev)[:, None]], 1)
+            dist.all_gather(gather_buf, rows_e)
     e1.record()
     barrier()
     e_ms = torch.tensor([max(e0.elapsed_time(e1), (time.perf_counter() - w0) * 1e3)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e_ms, op=dist.ReduceOp.MAX)
     e2e_value = world * B / (float(e_ms) / args.steps * 1e-3)
+    assert bool(np.isfinite(out["s_hat"].numpy()).all())
 
     # ---- roofline of the two hot kernels (events recorded inside the timed region) ------
     peaks = {}
@@ -295,6 +304,8 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "f16 operands, f32 accumulate",
             "data": "synthetic", "config": workload(args), "clocks": clk,
+            "quality": {"si_sdr_db_mean": float(rows[:, 1].mean()), "note": "random-init decoder (no trained weights ship with the "
+                        "reference): the number checks plumbing, not enhancement quality"},
             "e2e": {"value": e2e_value, "unit": "utt/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": launches,
             "roofline": {"kernel": "gvn_estep (decoder MLP + MH chain, %s)" % args.precision, "bound": "tensor",

@@ -42,6 +42,7 @@ int32_t launch_istft(const gvn_batch*, const float*, int, int, const int32_t*, f
 int32_t launch_dense(const float*, const float*, const float*, int, const float*, int, const float*, const float*, float,
                      int, int, int, float*, cudaStream_t);
 void set_profile_buffer(void*);
+int32_t launch_energy_ratios(const float*, const float*, const float*, int, int, const int32_t*, double*, cudaStream_t);
 int32_t launch_selftest_umma(const float*, const float*, int, int, int, float*, cudaStream_t);
 int32_t launch_pack_decoder(const float*, const float*, const float*, const float*, const float*, const float*, int, int,
                             int, void*, cudaStream_t);
@@ -164,6 +165,13 @@ int32_t gvn_dense(const float* W, const float* b, const float* in0, int32_t D0, 
   GVN_REQUIRE((mean == nullptr) == (std_ == nullptr), GVN_E_INVALID, "mean and std must both be given or both NULL");
   GVN_REQUIRE(act >= 0 && act <= 4, GVN_E_INVALID, "act=%d", act);
   return launch_dense(W, b, in0, D0, in1, D1, mean, std_, eps, D_out, NP, act, out, (cudaStream_t)stream);
+}
+
+int32_t gvn_energy_ratios(const float* est, const float* s, const float* n, int32_t B, int32_t T_stride, const int32_t* T,
+                          double* out, void* stream) {
+  GVN_REQUIRE(est && s && n && T && out, GVN_E_INVALID, "NULL pointer");
+  GVN_REQUIRE(B > 0 && T_stride > 0, GVN_E_INVALID, "B=%d T_stride=%d", B, T_stride);
+  return launch_energy_ratios(est, s, n, B, T_stride, T, out, (cudaStream_t)stream);
 }
 
 void gvn_debug_profile_buffer(void* dev_u64) { set_profile_buffer(dev_u64); }

@@ -82,6 +82,12 @@ __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.
 __device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float tanh_approx(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// two hidden units per MUFU instruction: the result is needed as an f16 pair (the next layer's A operand) anyway
+__device__ __forceinline__ uint32_t tanh_f16x2(float lo, float hi) {
+  uint32_t x = pack_f16(lo, hi), y;
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x));
+  return y;
+}
 
 // 2^t on the FMA/ALU pipes (Cody-Waite split + degree-6 minimax, ~1e-7 relative): takes MUFU.EX2
 // work off the special-function pipe, which bounds the chain epilogue
@@ -365,8 +371,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_estep_tc(const __grid_constant_
             const float2 t = *reinterpret_cast<const float2*>(sB2 + 64 * half + c0 + 2 * j);
             b0 = t.x; b1 = t.y;
           }
-          o[j] = pack_f16(tanh_approx(fmaf(__uint_as_float(r[2 * j]), W_SCALE_INV, b0)),
-                          tanh_approx(fmaf(__uint_as_float(r[2 * j + 1]), W_SCALE_INV, b1)));
+          o[j] = tanh_f16x2(fmaf(__uint_as_float(r[2 * j]), W_SCALE_INV, b0), fmaf(__uint_as_float(r[2 * j + 1]), W_SCALE_INV, b1));
         }
         tmem_st8(tlane + COL_A + (64 * half + c0) / 2, o);
       }

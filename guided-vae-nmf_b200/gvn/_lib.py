@@ -51,6 +51,7 @@ SIGNATURES = {
     "gvn_istft": (_i, [C.POINTER(GvnBatch), _p, _i, _i, _p, _p, _i, _p, _p]),
     "gvn_dense": (_i, [_p, _p, _p, _i, _p, _i, _p, _p, C.c_float, _i, _i, _i, _p, _p]),
     "gvn_init_nmf": (_i, [C.POINTER(GvnBatch), _p, _p, C.c_float, _p]),
+    "gvn_energy_ratios": (_i, [_p, _p, _p, _i, _i, _p, _p, _p]),
     "gvn_selftest_umma": (_i, [_p, _p, _i, _i, _i, _p, _p]),
     "gvn_debug_profile_buffer": (None, [_p]),
     "gvn_launch_count": (C.c_uint64, []),

@@ -209,17 +209,33 @@ def pinned_buffer(tag, shape, dtype=torch.float32):
     return buf
 
 
-def upload_waveforms(wavs, device, pinned=None):
-    """Packs B waveforms into one zero-padded (B, T_stride) f32 tensor on the device."""
+_DEVBUF = {}
+
+
+def device_buffer(tag, shape, dtype, device):
+    """Device-side landing buffer of an upload, allocated once per (tag, shape) and reused."""
+    key = (tag, tuple(shape), dtype, str(device))
+    buf = _DEVBUF.get(key)
+    if buf is None:
+        buf = torch.empty(*shape, dtype=dtype, device=device)
+        _DEVBUF[key] = buf
+    return buf
+
+
+def upload_waveforms(wavs, device, pinned=None, tag="wav"):
+    """Packs B waveforms into one zero-padded (B, T_stride) f32 tensor on the device (pinned staging
+    buffer and device buffer named by `tag`, so that two uploads can be in flight with two tags)."""
     B = len(wavs)
     T = [len(w) for w in wavs]
     T_stride = (max(T) + 3) // 4 * 4
-    host = pinned if pinned is not None else pinned_buffer("wav", (B, T_stride))
-    hn = host.numpy()
+    host = pinned if pinned is not None else pinned_buffer(tag, (B, T_stride))
     for b, w in enumerate(wavs):
-        hn[b, :T[b]] = np.asarray(w, dtype=np.float32)
-        hn[b, T[b]:] = 0
-    return host.to(device, non_blocking=True), T, T_stride
+        host[b, :T[b]].copy_(torch.from_numpy(np.ascontiguousarray(w)))      # f64 -> f32 conversion on the way
+        if T[b] < T_stride:
+            host[b, T[b]:] = 0
+    dev = device_buffer(tag, (B, T_stride), torch.float32, device)
+    dev.copy_(host, non_blocking=True)
+    return dev, T, T_stride
 
 
 def download(t, tag):
@@ -382,6 +398,19 @@ def wiener(batch, R, want_masks=False):
     WFn = torch.empty(batch.F, batch.NP, **f32) if want_masks else None
     check(lib.gvn_wiener(batch.struct(), int(R), _ptr(S), _ptr(Nn), _ptr(WFs), _ptr(WFn), _stream()))
     return S, Nn, WFs, WFn
+
+
+def energy_ratios(est, s_ref, n_ref, T):
+    """(SI-SDR, SI-SIR, SI-SAR) in dB of B signals (python/metrics.py:12-60) -> (B, 3) f64 device tensor.
+    est, s_ref, n_ref: (B, T_stride) f32 device tensors; T: per-utterance lengths (list or device i32 tensor)."""
+    lib = _lib.load()
+    B, T_stride = est.shape
+    assert s_ref.shape == est.shape and n_ref.shape == est.shape
+    Td = T if torch.is_tensor(T) else torch.tensor([int(v) for v in T], dtype=torch.int32, device=est.device)
+    out = torch.empty(B, 3, dtype=torch.float64, device=est.device)
+    check(lib.gvn_energy_ratios(_ptr(est.contiguous()), _ptr(s_ref.contiguous()), _ptr(n_ref.contiguous()), B, T_stride,
+                                _ptr(Td), _ptr(out), _stream()))
+    return out
 
 
 class KernelTimers:

@@ -53,25 +53,41 @@ class Enhancer:
             self.dec = E.PackedDecoder(vae, self.device)
         self._batches = {}          # batch state in HBM is allocated once per shape and reused (stream-ordered)
 
-    def upload(self, wavs, labels=None):
-        """Host -> device copy of one batch of inputs (pinned staging, async on the stream):
-        the waveforms and, for oracle-label M2, the (y_dim, N_b) label arrays."""
+    def upload(self, wavs, labels=None, refs=None, slot=0):
+        """Host -> device copy of one batch of inputs (pinned staging, async on the current stream): the
+        waveforms and, for oracle-label M2, the (y_dim, N_b) label arrays.  Binary labels travel as one
+        byte per bin and are widened on the device.  ``refs`` = (clean speech, noise) arrays (B, T) for the
+        quality metrics.  ``slot`` names the staging buffers (two slots allow an upload to overlap the
+        enhancement of the previous batch, see :meth:`enhance_many`)."""
         cfg, dev = self.cfg, self.device
         geo = [E.stft_geometry(len(w), cfg.fs, cfg.wlen_sec, cfg.hop_percent) for w in wavs]
         with torch.cuda.device(dev):
-            wav, T, T_stride = E.upload_waveforms(wavs, dev)
+            wav, T, T_stride = E.upload_waveforms(wavs, dev, tag="wav%d" % slot)
             y, nbytes = None, wav.numel() * 4
             if cfg.model == "M2" and labels is not None:
                 A = E.GVN_FRAME_ALIGN
                 off = np.cumsum([0] + [(g[3] + A - 1) // A * A for g in geo])
-                host = E.pinned_buffer("labels", (self.dec.y_dim, int(off[-1])))
+                binary = all(getattr(l, "dtype", None) == np.uint8 for l in labels)    # 0/1 masks may be passed as bytes
+                dt = torch.uint8 if binary else torch.float32
+                host = E.pinned_buffer("labels%d" % slot, (self.dec.y_dim, int(off[-1])), dt)
                 hn = host.numpy()
-                hn[:] = 0
                 for i, l in enumerate(labels):
-                    hn[:, off[i]:off[i] + geo[i][3]] = np.asarray(l, dtype=np.float32)
-                y = host.to(dev, non_blocking=True)
-                nbytes += y.numel() * 4
-        return dict(wav=wav, T=T, T_stride=T_stride, geo=geo, y=y, h2d_bytes=nbytes)
+                    hn[:, off[i]:off[i] + geo[i][3]] = l
+                    hn[:, off[i] + geo[i][3]:off[i + 1]] = 0
+                yd = E.device_buffer("labels%d" % slot, host.shape, dt, dev)
+                yd.copy_(host, non_blocking=True)
+                y = yd.float() if binary else yd
+                nbytes += host.numel() * host.element_size()
+            out = dict(wav=wav, T=T, T_stride=T_stride, geo=geo, y=y, h2d_bytes=nbytes)
+            if refs is not None:
+                for name, arr in zip(("ref_s", "ref_n"), refs):
+                    host = E.pinned_buffer("%s%d" % (name, slot), (len(wavs), T_stride))
+                    host[:, :arr.shape[1]].copy_(torch.from_numpy(np.ascontiguousarray(arr)))
+                    d = E.device_buffer("%s%d" % (name, slot), host.shape, torch.float32, dev)
+                    d.copy_(host, non_blocking=True)
+                    out[name] = d
+                    out["h2d_bytes"] += host.numel() * 4
+        return out
 
     def prepare(self, wavs, labels=None, seed=0, rand=None, uploaded=None):
         """STFT + initialisation of a batch.  ``labels``: None (M1 / classifier) or a list of
@@ -113,6 +129,51 @@ class Enhancer:
             s_hat = E.istft_from(b, S, b.T, b.T_stride, b.nfft, b.hop)
             n_hat = E.istft_from(b, Nn, b.T, b.T_stride, b.nfft, b.hop)
         return s_hat, n_hat, cost
+
+    def enhance_many(self, batches, seed=0):
+        """Pipelined end-to-end enhancement of a sequence of batches.  ``batches`` yields dicts with keys
+        ``wavs``, optionally ``labels`` and ``refs`` (clean speech, noise: adds the quality metrics).
+        The host packing and H2D copy of batch i+1 run on a second stream while batch i is enhanced; results
+        come back in pinned host buffers (valid until the next iteration).  Yields dicts with ``s_hat``,
+        ``n_hat`` (B, T_stride) f32, ``cost`` (niter, B) f64, ``metrics`` (B, 3) f64 or None, ``T``, byte counts."""
+        dev = self.device
+        main = torch.cuda.current_stream(dev)
+        copy = getattr(self, "_copy_stream", None)
+        if copy is None:
+            copy = self._copy_stream = torch.cuda.Stream(dev)
+        consumed = [None, None]                             # main-stream events: inputs of slot p have been read
+
+        def start_upload(item, slot):
+            with torch.cuda.stream(copy):
+                if consumed[slot] is not None:
+                    copy.wait_event(consumed[slot])
+                up = self.upload(item["wavs"], item.get("labels"), item.get("refs"), slot=slot)
+                ev = torch.cuda.Event()
+                ev.record(copy)
+            return up, ev
+
+        it = iter(batches)
+        nxt = next(it, None)
+        pending = start_upload(nxt, 0) if nxt is not None else None
+        i = 0
+        while pending is not None:
+            up, ev = pending
+            main.wait_event(ev)
+            b = self.prepare(None, None, seed=seed + i, uploaded=up)
+            consumed[i & 1] = torch.cuda.Event()
+            consumed[i & 1].record(main)
+            s_hat, n_hat, cost = self.run(b, seed=seed + i)
+            metrics = None
+            if "ref_s" in up:
+                metrics = E.download(E.energy_ratios(s_hat, up["ref_s"], up["ref_n"], b.T), "metrics")
+            out = dict(s_hat=E.download(s_hat, "s_hat"), n_hat=E.download(n_hat, "n_hat"), cost=E.download(cost, "cost"),
+                       metrics=metrics, T=b.T, h2d_bytes=up["h2d_bytes"],
+                       d2h_bytes=(s_hat.numel() + n_hat.numel()) * 4 + cost.numel() * 8 + (0 if metrics is None else metrics.numel() * 8))
+            nxt = next(it, None)                            # pack + copy the next batch while this one computes
+            pending = start_upload(nxt, (i + 1) & 1) if nxt is not None else None
+            main.synchronize()
+            yield out
+            i += 1
 
     def enhance(self, wavs, labels=None, seed=0):
         """Host waveforms in, host waveforms out (the end-to-end call)."""

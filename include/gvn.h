@@ -189,6 +189,12 @@ int32_t gvn_dense(const float* W, const float* b, const float* in0, int32_t D0, 
 int32_t gvn_init_nmf(const gvn_batch* batch /*HOST*/, const float* rand_W /*[B][F][K]*/,
                      const float* rand_H /*[K][NP]*/, float eps, void* stream);
 
+/* Quality metrics of B enhanced signals against their clean-speech and noise references:
+ * replaces energy_ratios / si_sdr_components (python/metrics.py:12-60).  est, s, n are
+ * [B][T_stride] f32 with true lengths T[b]; out is [B][3] f64 = (SI-SDR, SI-SIR, SI-SAR) in dB. */
+int32_t gvn_energy_ratios(const float* est, const float* s, const float* n, int32_t B, int32_t T_stride,
+                          const int32_t* T, double* out, void* stream);
+
 /* Hardware self test of the tensor-core plumbing used by gvn_estep in the f16 modes:
  * D[128][N] = A[128][K] @ W[N][K]^T through tcgen05.st (A -> TMEM), a packed shared-memory
  * image of W, tcgen05.mma and tcgen05.ld.  variant bit2 selects the 3-term hi/lo split. */

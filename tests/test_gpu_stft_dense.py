@@ -102,3 +102,22 @@ def test_classifier_hard_labels():
         ref = (clf(b.X2[:, b.cols(0)].T.cpu() / (1 + 1e-8)) > 0.5).float().T
     assert y.shape == (1, b.NP)
     np.testing.assert_array_equal(y[:, b.cols(0)].cpu().numpy(), ref.numpy())
+
+
+def test_energy_ratios_match_reference_metrics():
+    """gvn_energy_ratios against python/metrics.py:12-60 (float64 numpy) on ragged synthetic signals."""
+    from gvn import engine as E
+    from gvn.synth import synth_utterance
+    from python.metrics import energy_ratios
+    Ts = [64000, 50001, 777]
+    stride = 64000
+    rs = np.random.RandomState(3)
+    est = np.zeros((3, stride), np.float32); s = np.zeros_like(est); n = np.zeros_like(est)
+    for i, T in enumerate(Ts):
+        x, sp, no = synth_utterance(i, seed=9, T=T)
+        s[i, :T], n[i, :T] = sp, no
+        est[i, :T] = 0.7 * sp + 0.2 * no + 0.05 * rs.randn(T)
+    out = E.energy_ratios(torch.from_numpy(est).cuda(), torch.from_numpy(s).cuda(), torch.from_numpy(n).cuda(), Ts).cpu().numpy()
+    for i, T in enumerate(Ts):
+        ref = energy_ratios(est[i, :T].astype(np.float64), s[i, :T].astype(np.float64), n[i, :T].astype(np.float64))
+        np.testing.assert_allclose(out[i], ref, rtol=1e-9, atol=1e-9)
