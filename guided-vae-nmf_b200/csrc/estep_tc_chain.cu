@@ -51,7 +51,7 @@ constexpr int SROWS = 32;               // frequency rows per TMA box
 constexpr int STAGE_BYTES = SROWS * TM * 4;
 constexpr int MAX_STAGES = 8;
 #ifndef GVN_TC_DEFAULT_VARIANT
-#define GVN_TC_DEFAULT_VARIANT 1
+#define GVN_TC_DEFAULT_VARIANT 3
 #endif
 constexpr float W_SCALE_INV = 1.0f / 256.0f;
 constexpr float LOG2E = 1.4426950408889634f;
@@ -261,6 +261,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_estep_tc(const __grid_constant_
     const float g = valid ? p.g[n] : 1.f;
     uint32_t n_d0 = 0, n_d1 = 0, n_hf = 0, n_dec = 0;
     uint32_t slot = 0, ph = 0;                            // ring position of the next stage
+    uint32_t ring_ok = 0;                                 // early probe result for that stage (V_PROBE)
     unsigned long long pc[PROF_ON ? 12 : 1] = {0}, pt = PROF_ON ? clock64() : 0ull;
 #define PROF(i) do { if constexpr (PROF_ON) { const unsigned long long t_ = clock64(); pc[i] += t_ - pt; pt = t_; } } while (0)
     constexpr bool PRE = (L16 == 16);
@@ -402,7 +403,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_estep_tc(const __grid_constant_
         // one stage = this thread's 16 bins of a 32-row ring box; the accumulator columns of stage s+1
         // are requested from TMEM before the math of stage s (two register sets, statically indexed)
         constexpr bool V_PF = (VAR & 1) != 0;             // prefetch the next stage's accumulator columns
-        constexpr bool V_PRE = (VAR & 2) != 0;            // all shared-memory loads of a stage before its math
+        constexpr bool V_PRE = false;
+        constexpr bool V_PROBE = (VAR & 2) != 0;          // probe the next stage's ring barrier before this stage's math
         constexpr bool V_POLY = (VAR & 4) != 0;           // every second exp on the FMA pipe
         auto stage = [&](uint32_t (&r)[16], uint32_t (&rn)[16], int s_) {
           const int f0 = c * 128 + s_ * SROWS + 16 * half;
@@ -410,9 +412,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_estep_tc(const __grid_constant_
           if (!V_PF) tmem_ld16(tlane + acc_col + s_ * SROWS, r);
           if (ENERGY) {
             PROF(7);
-            mbar_wait(bar_full + slot, ph);
+            if (!(V_PROBE && ring_ok)) mbar_wait(bar_full + slot, ph);
             PROF(6);
             xv = reinterpret_cast<const uint32_t*>(sRing + (size_t)slot * STAGE_BYTES) + (16 * half) * TM + row;
+            if (V_PROBE) {                                 // is the stage after this one already there?
+              uint32_t ns = slot + 1, np_ = ph;
+              if (ns == (uint32_t)p.nstage) { ns = 0; np_ ^= 1; }
+              ring_ok = mbar_test(bar_full + ns, np_);
+            }
           }
           if (V_PF && s_ + 1 < nst) tmem_ld16(tlane + acc_col + (s_ + 1) * SROWS, rn);   // prefetch
           float* vo = STORE ? vs_out + tile_off(f0, n, F) : nullptr;              // column-tile order: bin stride = 8 floats

@@ -33,7 +33,7 @@ __global__ void k(float* out, long long* cyc, int iters) {
       }
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < (MODE >= 4 ? 0 : 8); ++j) {
       float2 bb;
       if (MODE == 3) { bb.x = bv[2 * j]; bb.y = bv[2 * j + 1]; } else bb = *reinterpret_cast<const float2*>(b3 + 16 * half + 2 * j);
       float v0, v1;
@@ -45,6 +45,24 @@ __global__ void k(float* out, long long* cyc, int iters) {
       if (MODE != 1) sl += lg2a(pr); else sl += pr;
       const float qn = fmaf(__uint_as_float(w0 & 0xffff0000u), b, __uint_as_float(w1 & 0xffff0000u) * a);
       if (MODE != 1) sr = fmaf(qn, rcpa(pr), sr); else sr = fmaf(qn, pr, sr);
+    }
+    if (MODE == 4 || MODE == 5) {   // packed f32x2 arithmetic; MODE 5: x2 taken unmasked from the word
+      const unsigned* x = xv + 16 * half * 128 + row;
+      float2 acc2 = make_float2(sl, sr);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float2 bb = *reinterpret_cast<const float2*>(b3 + 16 * half + 2 * j);
+        const float2 t = __ffma2_rn(make_float2(r[2 * j], r[2 * j + 1]), make_float2(0.0056f, 0.0056f), bb);
+        const float v0 = ex2a(t.x), v1 = ex2a(t.y);
+        const unsigned w0 = x[(2 * j) * 128], w1 = x[(2 * j + 1) * 128];
+        const float2 ab = __ffma2_rn(make_float2(g, g), make_float2(v0, v1), make_float2(__uint_as_float(w0 << 16), __uint_as_float(w1 << 16)));
+        const float pr = ab.x * ab.y;
+        const float x0 = MODE == 5 ? __uint_as_float(w0) : __uint_as_float(w0 & 0xffff0000u);
+        const float x1 = MODE == 5 ? __uint_as_float(w1) : __uint_as_float(w1 & 0xffff0000u);
+        const float qn = fmaf(x0, ab.y, x1 * ab.x);
+        acc2 = __ffma2_rn(make_float2(1.0f, qn), make_float2(lg2a(pr), rcpa(pr)), acc2);
+      }
+      sl = acc2.x; sr = acc2.y;
     }
     r[it & 15] += sl * 1e-30f;      // loop-carried, keeps everything live
   }
@@ -63,10 +81,10 @@ void run(const char* name, int threads) {
   long long h[148]; cudaMemcpy(h, cyc, 148 * 8, cudaMemcpyDeviceToHost);
   double c = 0; for (int i = 0; i < 148; ++i) c += h[i]; c /= 148;
   printf("%-28s %4d threads (%d warps/scheduler): %.0f cycles per 16-bin group per scheduler (MUFU floor %d)\n", name, threads, threads / 128,
-         c / iters, (MODE == 0 || MODE == 3) ? 32 * 8 * (threads / 128) : (MODE == 1 ? 16 * 8 * (threads / 128) : 16 * 8 * (threads / 128)));
+         c / iters, (MODE == 0 || MODE >= 3) ? 32 * 8 * (threads / 128) : (MODE == 1 ? 16 * 8 * (threads / 128) : 16 * 8 * (threads / 128)));
   cudaFree(out); cudaFree(cyc);
 }
 int main() {
-  for (int th : {128, 256, 512}) { run<0>("full (ex2+lg2+rcp)", th); run<3>("full, LDS.128 swizzled", th); run<1>("ex2 only", th); run<2>("lg2+rcp only", th); }
+  for (int th : {128, 256, 512}) { run<0>("full (ex2+lg2+rcp)", th); run<3>("full, LDS.128 swizzled", th); run<4>("full, packed f32x2", th); run<5>("full, packed + unmasked x2", th); run<1>("ex2 only", th); run<2>("lg2+rcp only", th); }
   return 0;
 }
