@@ -256,10 +256,12 @@ __global__ void __launch_bounds__(256) k_wiener(int F, int NP, int R, const int3
     if (frame_utt[gn] >= 0) {
       const float gg = g[gn], vb = Vb[i];
       for (int r = 0; r < R; ++r) {
-        float sc = gg * Vs[tile_off(f, gn, F) + (size_t)r * slab], w = Vs_w[(size_t)r * NP + gn];
-        float vx = sc + vb;
-        ws = fmaf(w, sc / vx, ws);
-        wn = fmaf(w, vb / vx, wn);
+        const float w = Vs_w[(size_t)r * NP + gn];
+        if (w == 0.f) continue;                                 // dead slot (rejected proposal)
+        const float sc = gg * Vs[tile_off(f, gn, F) + (size_t)r * slab];
+        const float wi = w * __frcp_rn(sc + vb);
+        ws = fmaf(wi, sc, ws);
+        wn = fmaf(wi, vb, wn);
       }
       ws /= (float)R;
       wn /= (float)R;
@@ -277,32 +279,39 @@ __global__ void k_init_nmf_w(size_t n, const float* __restrict__ rnd, float eps,
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) W[i] = fmaxf(rnd[i], eps);
 }
-__global__ void k_init_nmf_cols(int F, int K, int NP, const int32_t* __restrict__ frame_utt,
-                                const float* __restrict__ rndH, float eps, const float* __restrict__ W,
-                                float* __restrict__ H, float* __restrict__ g, float* __restrict__ Vb,
-                                float* __restrict__ X2, float2* __restrict__ Xc, float* __restrict__ X2t) {
-  const int gn = blockIdx.x * blockDim.x + threadIdx.x;
-  if (gn >= NP) return;
+// one CTA per 32-frame group: H, g and the padding constants by the first warp, then Vb = W @ H and the
+// column-tile copy of X2 with threads over (frequency, frame) -- coalesced along the frame axis
+__global__ void __launch_bounds__(256) k_init_nmf_cols(int F, int K, int NP, const int32_t* __restrict__ frame_utt,
+                                                       const float* __restrict__ rndH, float eps, const float* __restrict__ W,
+                                                       float* __restrict__ H, float* __restrict__ g, float* __restrict__ Vb,
+                                                       float* __restrict__ X2, float2* __restrict__ Xc, float* __restrict__ X2t) {
+  __shared__ float h_s[GVN_MAX_K][32];
+  const int lane = threadIdx.x & 31, fw = threadIdx.x >> 5;
+  const int gn = blockIdx.x * 32 + lane;
   const int b = frame_utt[gn];
-  g[gn] = 1.f;
-  if (b < 0) {   // padding frame: benign constants, never updated
-    for (int k = 0; k < K; ++k) H[(size_t)k * NP + gn] = 1.f;
-    for (int f = 0; f < F; ++f) {
-      Vb[(size_t)f * NP + gn] = 1.f;
-      X2[(size_t)f * NP + gn] = 1.f;
-      if (X2t != nullptr) X2t[tile_off(f, gn, F)] = 1.f;
-      if (Xc != nullptr) Xc[(size_t)f * NP + gn] = make_float2(0.f, 0.f);
+  if (fw == 0) {
+    g[gn] = 1.f;
+    for (int k = 0; k < K; ++k) {
+      const float h = b < 0 ? 1.f : fmaxf(rndH[(size_t)k * NP + gn], eps);
+      H[(size_t)k * NP + gn] = h;
+      h_s[k][lane] = h;
     }
-    return;
   }
-  float h[GVN_MAX_K];
-  for (int k = 0; k < K; ++k) { h[k] = fmaxf(rndH[(size_t)k * NP + gn], eps); H[(size_t)k * NP + gn] = h[k]; }
-  const float* w = W + (size_t)b * F * K;
-  for (int f = 0; f < F; ++f) {
-    float vb = 0.f;
-    for (int k = 0; k < K; ++k) vb = fmaf(w[(size_t)f * K + k], h[k], vb);
-    Vb[(size_t)f * NP + gn] = vb;
-    if (X2t != nullptr) X2t[tile_off(f, gn, F)] = X2[(size_t)f * NP + gn];   // column-tile copy for the M-step
+  __syncthreads();
+  const float* w = W + (size_t)(b < 0 ? 0 : b) * F * K;
+  for (int f = fw; f < F; f += 8) {
+    const size_t o = (size_t)f * NP + gn;
+    if (b < 0) {   // padding frame: benign constants, never updated
+      Vb[o] = 1.f;
+      X2[o] = 1.f;
+      if (X2t != nullptr) X2t[tile_off(f, gn, F)] = 1.f;
+      if (Xc != nullptr) Xc[o] = make_float2(0.f, 0.f);
+    } else {
+      float vb = 0.f;
+      for (int k = 0; k < K; ++k) vb = fmaf(__ldg(w + (size_t)f * K + k), h_s[k][lane], vb);
+      Vb[o] = vb;
+      if (X2t != nullptr) X2t[tile_off(f, gn, F)] = X2[o];   // column-tile copy for the M-step
+    }
   }
 }
 
@@ -365,7 +374,7 @@ int32_t launch_init_nmf(const gvn_batch* b, const float* rand_W, const float* ra
   k_init_nmf_w<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, rand_W, eps, b->W);
   int32_t rc = check_launch("k_init_nmf_w");
   if (rc) return rc;
-  k_init_nmf_cols<<<(b->NP + 127) / 128, 128, 0, st>>>(b->F, b->K, b->NP, b->frame_utt, rand_H, eps, b->W, b->H, b->g,
+  k_init_nmf_cols<<<b->NP / 32, 256, 0, st>>>(b->F, b->K, b->NP, b->frame_utt, rand_H, eps, b->W, b->H, b->g,
                                                        b->Vb, b->X2, reinterpret_cast<float2*>(b->Xc), b->X2t);
   return check_launch("k_init_nmf_cols");
 }

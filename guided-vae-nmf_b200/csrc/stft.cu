@@ -1,5 +1,5 @@
 // STFT power spectrum and ISTFT, framing / window / |.|^2 / overlap-add fused around a
-// shared-memory radix-2 FFT (n_fft a power of two, <= 4096).
+// shared-memory radix-2 FFT (n_fft a power of two, <= 2048).
 //
 // Replaces python/processing/stft.py:16-63 and :66-102 of the reference, i.e. the librosa
 // semantics those wrappers select: reflect centring by n_fft/2, periodic Hann, rFFT without
@@ -12,24 +12,36 @@ namespace gvn {
 namespace {
 
 constexpr int FFT_THREADS = 256;
+constexpr int FPB = 8;                  // frames per CTA pass: stores cover whole 32-byte sectors of the frame-minor arrays
 
 __device__ __forceinline__ float hann_periodic(int i, int n) { return 0.5f - 0.5f * cospif(2.0f * (float)i / (float)n); }
 
 __device__ __forceinline__ int bit_reverse(int x, int bits) { return (int)(__brev((unsigned)x) >> (32 - bits)); }
 
-// in-place radix-2 decimation-in-time FFT on bit-reversed input, forward (e^{-i...}) transform
-__device__ void fft_inplace(float2* s, int n, int bits) {
+// twiddle table tw[k] = exp(-2 pi i k / n), k < n/2, once per CTA
+__device__ void fft_twiddles(float2* tw, int n) {
+  for (int k = threadIdx.x; k < n / 2; k += FFT_THREADS) {
+    float sn, cs;
+    sincospif(-2.0f * (float)k / (float)n, &sn, &cs);
+    tw[k] = make_float2(cs, sn);
+  }
+}
+
+// in-place radix-2 decimation-in-time FFTs of FPB bit-reversed sequences s[q][n] side by side, forward transform
+__device__ void fft_inplace(float2* s, const float2* __restrict__ tw, int n, int bits) {
+  const int nb = n / 2 * FPB;                                   // butterflies per stage
   for (int st = 1; st <= bits; ++st) {
-    const int half = 1 << (st - 1);
-    for (int idx = threadIdx.x; idx < n / 2; idx += FFT_THREADS) {
-      const int grp = idx >> (st - 1), pos = idx & (half - 1);
+    const int half = 1 << (st - 1), tstep = n >> st;
+    for (int idx = threadIdx.x; idx < nb; idx += FFT_THREADS) {
+      const int q = idx / (n / 2), bi = idx - q * (n / 2);
+      const int grp = bi >> (st - 1), pos = bi & (half - 1);
+      float2* sq = s + (size_t)q * n;
       const int i = (grp << st) + pos, j = i + half;
-      float sn, cs;
-      sincospif(-(float)pos / (float)half, &sn, &cs);
-      const float2 a = s[i], b = s[j];
-      const float2 t = make_float2(cs * b.x - sn * b.y, cs * b.y + sn * b.x);
-      s[i] = make_float2(a.x + t.x, a.y + t.y);
-      s[j] = make_float2(a.x - t.x, a.y - t.y);
+      const float2 w = tw[pos * tstep];
+      const float2 a = sq[i], b = sq[j];
+      const float2 t = make_float2(w.x * b.x - w.y * b.y, w.x * b.y + w.y * b.x);
+      sq[i] = make_float2(a.x + t.x, a.y + t.y);
+      sq[j] = make_float2(a.x - t.x, a.y - t.y);
     }
     __syncthreads();
   }
@@ -41,25 +53,29 @@ __global__ void __launch_bounds__(FFT_THREADS) k_stft_power(int F, int NP, int n
                                                            const float* __restrict__ wav, int T_stride,
                                                            const int32_t* __restrict__ T, const int32_t* __restrict__ end_pad,
                                                            float2* __restrict__ Xc, float* __restrict__ X2) {
-  extern __shared__ float2 s_fft[];
-  for (int gn = blockIdx.x; gn < NP; gn += gridDim.x) {
-    const int b = frame_utt[gn];
-    if (b < 0) continue;                       // uniform per CTA
-    const int j = gn - frame_off[b];
+  extern __shared__ float2 s_fft[];                             // [FPB][n_fft] | twiddles [n_fft/2]
+  float2* tw = s_fft + (size_t)FPB * n_fft;
+  fft_twiddles(tw, n_fft);
+  for (int g0 = blockIdx.x * FPB; g0 < NP; g0 += gridDim.x * FPB) {
+    const int b = frame_utt[g0];                                // groups of 8 frames never straddle utterances
+    if (b < 0) continue;                                        // uniform per CTA
     const int Tb = T[b], Tx = Tb + (end_pad[b] ? hop : 0);
     const float* x = wav + (size_t)b * T_stride;
-    for (int i = threadIdx.x; i < n_fft; i += FFT_THREADS) {
+    for (int e = threadIdx.x; e < FPB * n_fft; e += FFT_THREADS) {
+      const int q = e / n_fft, i = e - q * n_fft, j = g0 + q - frame_off[b];
       int idx = j * hop + i - n_fft / 2;
-      if (idx < 0) idx = -idx;                 // numpy 'reflect' (no edge repeat)
+      if (idx < 0) idx = -idx;                                  // numpy 'reflect' (no edge repeat)
       if (idx >= Tx) idx = 2 * (Tx - 1) - idx;
-      float v = (idx >= 0 && idx < Tb) ? x[idx] : 0.f;
-      s_fft[bit_reverse(i, bits)] = make_float2(v * hann_periodic(i, n_fft), 0.f);
+      const float v = (idx >= 0 && idx < Tb) ? x[idx] : 0.f;
+      s_fft[(size_t)q * n_fft + bit_reverse(i, bits)] = make_float2(v * hann_periodic(i, n_fft), 0.f);
     }
     __syncthreads();
-    fft_inplace(s_fft, n_fft, bits);
-    for (int f = threadIdx.x; f < F; f += FFT_THREADS) {
-      const float2 v = s_fft[f];
-      const size_t o = (size_t)f * NP + gn;
+    fft_inplace(s_fft, tw, n_fft, bits);
+    for (int e = threadIdx.x; e < F * FPB; e += FFT_THREADS) {
+      const int f = e / FPB, q = e - f * FPB;                   // consecutive threads -> consecutive frames
+      if (frame_utt[g0 + q] < 0) continue;
+      const float2 v = s_fft[(size_t)q * n_fft + f];
+      const size_t o = (size_t)f * NP + g0 + q;
       Xc[o] = v;
       X2[o] = v.x * v.x + v.y * v.y;
     }
@@ -72,25 +88,30 @@ __global__ void __launch_bounds__(FFT_THREADS) k_istft_frames(int F, int NP, int
                                                              const int32_t* __restrict__ frame_utt,
                                                              const float2* __restrict__ S, float* __restrict__ ws) {
   extern __shared__ float2 s_fft[];
-  for (int gn = blockIdx.x; gn < NP; gn += gridDim.x) {
-    if (frame_utt[gn] < 0) continue;
+  float2* tw = s_fft + (size_t)FPB * n_fft;
+  fft_twiddles(tw, n_fft);
+  for (int g0 = blockIdx.x * FPB; g0 < NP; g0 += gridDim.x * FPB) {
+    if (frame_utt[g0] < 0) continue;
     // ifft(Y) = conj(fft(conj(Y)))/n with Y the Hermitian extension; the imaginary parts of
     // the DC and Nyquist bins are ignored, as numpy's irfft does
-    for (int k = threadIdx.x; k < n_fft; k += FFT_THREADS) {
+    for (int e = threadIdx.x; e < n_fft * FPB; e += FFT_THREADS) {
+      const int k = e / FPB, q = e - k * FPB;                   // consecutive threads -> consecutive frames
       float2 v;
       if (k <= n_fft / 2) {
-        v = S[(size_t)k * NP + gn];
-        v.y = (k == 0 || k == n_fft / 2) ? 0.f : -v.y;      // conj(Y[k])
+        v = S[(size_t)k * NP + g0 + q];
+        v.y = (k == 0 || k == n_fft / 2) ? 0.f : -v.y;          // conj(Y[k])
       } else {
-        v = S[(size_t)(n_fft - k) * NP + gn];               // conj(conj(S)) = S
+        v = S[(size_t)(n_fft - k) * NP + g0 + q];               // conj(conj(S)) = S
       }
-      s_fft[bit_reverse(k, bits)] = v;
+      s_fft[(size_t)q * n_fft + bit_reverse(k, bits)] = v;
     }
     __syncthreads();
-    fft_inplace(s_fft, n_fft, bits);
+    fft_inplace(s_fft, tw, n_fft, bits);
     const float inv_n = 1.0f / (float)n_fft;
-    for (int i = threadIdx.x; i < n_fft; i += FFT_THREADS)
-      ws[(size_t)gn * n_fft + i] = s_fft[i].x * inv_n * hann_periodic(i, n_fft);
+    for (int e = threadIdx.x; e < FPB * n_fft; e += FFT_THREADS) {
+      const int q = e / n_fft, i = e - q * n_fft;
+      if (frame_utt[g0 + q] >= 0) ws[(size_t)(g0 + q) * n_fft + i] = s_fft[e].x * inv_n * hann_periodic(i, n_fft);
+    }
     __syncthreads();
   }
 }
@@ -174,10 +195,17 @@ int32_t launch_energy_ratios(const float* est, const float* s, const float* n, i
 int32_t launch_stft_power(const gvn_batch* b, const float* wav, int T_stride, const int32_t* T, const int32_t* end_pad,
                           int n_fft, int hop, cudaStream_t st) {
   int bits = log2_exact(n_fft);
-  GVN_REQUIRE(bits >= 4 && bits <= 12, GVN_E_UNSUPPORTED_SHAPE, "n_fft=%d must be a power of two in [16,4096]", n_fft);
+  GVN_REQUIRE(bits >= 4 && bits <= 11, GVN_E_UNSUPPORTED_SHAPE, "n_fft=%d must be a power of two in [16,2048]", n_fft);
   GVN_REQUIRE(b->F == n_fft / 2 + 1, GVN_E_INVALID, "F=%d does not match n_fft=%d", b->F, n_fft);
-  int grid = b->NP < 148 * 8 ? b->NP : 148 * 8;
-  k_stft_power<<<grid, FFT_THREADS, (size_t)n_fft * sizeof(float2), st>>>(
+  const size_t smem = ((size_t)FPB * n_fft + n_fft / 2) * sizeof(float2);
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_stft_power, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(GVN_E_CUDA, "k_stft_power smem attr: %s", cudaGetErrorString(e));
+    smem_set = smem;
+  }
+  int grid = b->NP / FPB < 148 * 3 ? b->NP / FPB : 148 * 3;
+  k_stft_power<<<grid, FFT_THREADS, smem, st>>>(
       b->F, b->NP, n_fft, bits, hop, b->frame_utt, b->frame_off, wav, T_stride, T, end_pad,
       reinterpret_cast<float2*>(b->Xc), b->X2);
   return check_launch("k_stft_power");
@@ -188,11 +216,18 @@ size_t istft_workspace_bytes(const gvn_batch* b, int n_fft) { return (size_t)b->
 int32_t launch_istft(const gvn_batch* b, const float* S, int n_fft, int hop, const int32_t* out_len, float* out,
                      int T_stride, void* workspace, cudaStream_t st) {
   int bits = log2_exact(n_fft);
-  GVN_REQUIRE(bits >= 4 && bits <= 12, GVN_E_UNSUPPORTED_SHAPE, "n_fft=%d must be a power of two in [16,4096]", n_fft);
+  GVN_REQUIRE(bits >= 4 && bits <= 11, GVN_E_UNSUPPORTED_SHAPE, "n_fft=%d must be a power of two in [16,2048]", n_fft);
   GVN_REQUIRE(b->F == n_fft / 2 + 1, GVN_E_INVALID, "F=%d does not match n_fft=%d", b->F, n_fft);
   float* ws = reinterpret_cast<float*>(workspace);
-  int grid = b->NP < 148 * 8 ? b->NP : 148 * 8;
-  k_istft_frames<<<grid, FFT_THREADS, (size_t)n_fft * sizeof(float2), st>>>(b->F, b->NP, n_fft, bits, b->frame_utt,
+  const size_t smem = ((size_t)FPB * n_fft + n_fft / 2) * sizeof(float2);
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_istft_frames, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(GVN_E_CUDA, "k_istft_frames smem attr: %s", cudaGetErrorString(e));
+    smem_set = smem;
+  }
+  int grid = b->NP / FPB < 148 * 3 ? b->NP / FPB : 148 * 3;
+  k_istft_frames<<<grid, FFT_THREADS, smem, st>>>(b->F, b->NP, n_fft, bits, b->frame_utt,
                                                                            reinterpret_cast<const float2*>(S), ws);
   int32_t rc = check_launch("k_istft_frames");
   if (rc) return rc;
