@@ -59,13 +59,19 @@ def build_model(F=513, y_dim=513, L=16):
     return vae
 
 
-def make_inputs(n, first, T=64000):
-    """Synthetic utterances + oracle IBM labels, host side."""
+def make_inputs(n, first, T=64000, cpu_only=False):
+    """Synthetic utterances + oracle IBM labels (clean_speech_IBM of the clean
+    speech STFT, scripts/evaluate_M2_ibm.py:133-134).  The product arm computes that STFT with the
+    library's own kernel; only the CPU reference arm (cpu_only) uses the oracle's numpy STFT."""
     from gvn.synth import synth_batch
-    from oracle import stft_oracle                       # input preparation only (labels)
     from python.processing.target import clean_speech_IBM
+    if cpu_only:
+        from oracle import stft_oracle
+        stft = stft_oracle.stft
+    else:
+        from python.processing.stft import stft
     x, s, nz = synth_batch(n, seed=0, T=T, first=first)
-    labels = [clean_speech_IBM(stft_oracle.stft(si, dtype="complex64", **STFT_KW), 0.999, 0.999).astype(np.uint8) for si in s]
+    labels = [clean_speech_IBM(stft(si, dtype="complex64", **STFT_KW), 0.999, 0.999).astype(np.uint8) for si in s]
     return x, s, nz, labels                                  # binary masks as bytes (0/1), waveforms float64
 
 
@@ -138,7 +144,7 @@ def run_reference(args):
     cores = os.cpu_count()
     torch.set_num_threads(cores)
     vae = build_model()
-    x, s, _, _ = make_inputs(1, 0)
+    x, s, _, _ = make_inputs(1, 0, cpu_only=True)
     for _ in range(args.warmup):
         cpu_reference_utterance(x[0], s[0], vae, args, max(1, args.niter // 20))
     t0 = time.perf_counter()
