@@ -19,8 +19,12 @@
 //     word per (f, frame) (bf16 pair; both appear on the two sides of the acceptance ratio, so the
 //     rounding is a fixed perturbation of the target density, not noise) and stream through a TMA
 //     ring of [32 frequency rows][128 frames] boxes, produced by a dedicated warp;
-//   * the epilogue is MUFU-bound (exp per bin, log and reciprocal of Vx): bins are processed in
-//     pairs, log a + log b = log(ab) and x/a + y/b = (xb + ya)/(ab), one lg2 and one rcp per pair.
+//   * the epilogue lives on the special-function pipe (exp per bin, log and reciprocal of Vx, 8 cycles
+//     per warp instruction and scheduler): bins are processed in pairs, log a + log b = log(ab) and
+//     x/a + y/b = (xb + ya)/(ab), one lg2 and one rcp per pair; tanh as tanh.approx.f16x2;
+//   * the per-frame bias of the first layer (label projection + b1) sits in TMEM for the whole chain;
+//     the proposal noise and log u of step m+1 are drawn by the warps that idle while the owners
+//     accept/propose in step m and handed over through TMEM (L <= 16).
 // Kept samples: slot r of Vs receives the proposal of kept step r (speculative store from the
 // epilogue); Vs_w[r][n] is the multiplicity of slot r (0 when that proposal was rejected, k+1 when
 // the k following proposals were) -- see include/gvn.h.

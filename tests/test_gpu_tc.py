@@ -96,3 +96,43 @@ def test_tc_philox_matches_fp32_statistics():
     assert np.all(np.isfinite(res["f16"][0]))
     np.testing.assert_allclose(res["f16"][0], res["fp32"][0], rtol=1e-2)
     assert np.mean(np.abs(res["f16"][1] - res["fp32"][1])) < 0.02
+
+
+@pytest.mark.parametrize("L,y_dim", [(32, 513), (32, 0), (8, 1)])
+def test_tc_chain_other_latent_dims(L, y_dim):
+    """z_dim = 32 is what the evaluate scripts themselves use (scripts/evaluate_M2_ibm.py:33-38); the
+    tensor-core chain pads L to a multiple of 16.  Same noise, same forced decisions: f16 chain vs fp32 chain."""
+    from gvn import engine as E
+    from python.models.models import DeepGenerativeModel, VariationalAutoencoder
+    torch.manual_seed(3)
+    F, N, K, R, burnin = 513, 70, 6, 4, 5
+    vae = (VariationalAutoencoder([F, L, [128, 128]]) if y_dim == 0 else DeepGenerativeModel([F, y_dim, L, [128, 128]], None)).eval()
+    with torch.no_grad():
+        vae.decoder.reconstruction.bias.copy_(torch.linspace(-6.0, -1.0, F))
+    dec = E.PackedDecoder(vae, "cuda:0")
+    g = torch.Generator(device="cuda").manual_seed(5)
+    steps = R + burnin
+    eps = torch.randn(steps, L, 96, generator=g, device="cuda")
+    u = torch.rand(steps, 96, generator=g, device="cuda").clamp_(1e-6, 1.0)
+    forced = (torch.rand(steps, 96, generator=g, device="cuda") < 0.7).to(torch.uint8)
+    y = None if y_dim == 0 else (torch.rand(y_dim, 96, generator=g, device="cuda") > 0.5).float()
+    z0 = torch.randn(L, 96, generator=g, device="cuda") * 0.5
+    out = {}
+    for prec in ("fp32", "f16"):
+        b = E.Batch([N], F, K, L, R, "cuda:0", with_complex=False)
+        b.X2.copy_(torch.rand(F, b.NP, generator=torch.Generator(device="cuda").manual_seed(9), device="cuda") * 2 + 1e-3)
+        E.init_nmf(b, 1e-8, generator=torch.Generator(device="cuda").manual_seed(11))
+        E.set_labels(b, dec, y)
+        b.Z.copy_(z0)
+        acc, dec_, cnt, zs = E.estep(b, dec, burnin, R, 0.01, prec, eps=eps, u=u, forced=forced, trace=True)
+        torch.cuda.synchronize()
+        c = b.cols(0)
+        out[prec] = dict(acc=acc[:, c].cpu().numpy(), Z=b.Z[:, c].cpu().numpy(), Vs=b.expand_samples(R, 0).cpu().numpy(),
+                         w=b.Vs_w[:R, c].cpu().numpy(), zs=zs[..., c].cpu().numpy())
+    a, t = out["fp32"], out["f16"]
+    np.testing.assert_array_equal(t["w"], a["w"])
+    assert np.all(a["w"].sum(0) == R)                                       # multiplicities add up to R for every frame
+    np.testing.assert_allclose(t["Z"], a["Z"], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(t["zs"], a["zs"], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(t["Vs"], a["Vs"], rtol=5e-3)
+    np.testing.assert_allclose(t["acc"], a["acc"], atol=0.25, rtol=2e-2)
