@@ -155,13 +155,13 @@ __global__ void __launch_bounds__(256) k_tile_meta(int K, int R, int NP, const f
 constexpr int WROWS = 64;             // frequency rows per CTA
 constexpr int WCT = WROWS * NB;       // 512 compute threads
 constexpr int WT = WCT + 32;          // + producer warp
-constexpr int WS = 4;                 // ring stages (two CTAs per SM: 8 stages of ~23 KB in flight)
+constexpr int WS = 4;                 // ring stages at most (two CTAs per SM: 8 stages of ~23 KB in flight at R = 10)
 
 // floats of one ring stage: (R+1) planes of [WROWS][NB] + column data (H rows, g, multiplicities)
 __host__ __device__ inline int w_stage_floats(int K, int R) { return ((R + 1) * WROWS * NB + (K + 1 + R) * NB + 31) / 32 * 32; }
 
 template <int KMAX, int RT>
-__global__ void __launch_bounds__(WT, 2) k_w_v2(int F, int K, int NP, int R_rt, const int32_t* __restrict__ frame_off,
+__global__ void __launch_bounds__(WT, (KMAX > 16 ? 1 : 2)) k_w_v2(int F, int K, int NP, int R_rt, int ws, const int32_t* __restrict__ frame_off,
                                                 const int32_t* __restrict__ n_frames, const float* __restrict__ X2t,
                                                 const float* __restrict__ Vs, const float* __restrict__ Mt,
                                                 const float* __restrict__ W, float* __restrict__ Wun) {
@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(WT, 2) k_w_v2(int F, int K, int NP, int R_rt, 
   const int SSt = w_stage_floats(K, R);
 
   if (tid == 0) {
-    for (int s = 0; s < WS; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, WCT / 32); }
+    for (int s = 0; s < ws; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, WCT / 32); }
     fence_mbar_init();
   }
   __syncthreads();
@@ -188,8 +188,8 @@ __global__ void __launch_bounds__(WT, 2) k_w_v2(int F, int K, int NP, int R_rt, 
     // ================= producer warp: lane p copies plane p, lane R+1 the column data =================
     const uint32_t blk = (uint32_t)rows * NB * 4;
     for (int ti = 0; ti < ntile; ++ti) {
-      const int s = ti % WS;
-      if (ti >= WS) mbar_wait(empty + s, ((ti / WS) - 1) & 1);
+      const int s = ti % ws;
+      if (ti >= ws) mbar_wait(empty + s, ((ti / ws) - 1) & 1);
       float* dst = smw + (size_t)s * SSt;
       if (lane == 0) mbar_expect_tx(full + s, blk * (R + 1) + (uint32_t)MR * NB * 4);
       __syncwarp();
@@ -210,8 +210,8 @@ __global__ void __launch_bounds__(WT, 2) k_w_v2(int F, int K, int NP, int R_rt, 
   for (int k = 0; k < KMAX; ++k) { w[k] = (k < K && rowok) ? W[((size_t)b * F + f) * K + k] : 0.f; num[k] = den[k] = 0.f; }
 
   for (int ti = 0; ti < ntile; ++ti) {
-    const int s = ti % WS;
-    mbar_wait(full + s, (ti / WS) & 1);
+    const int s = ti % ws;
+    mbar_wait(full + s, (ti / ws) & 1);
     if (rowok) {
       const float* st = smw + (size_t)s * SSt;
       const float* vs = st + rl * NB + n;
@@ -618,6 +618,201 @@ __global__ void __launch_bounds__(CTT, 1) k_cols_v1(ColsArgs p) {
   }
 }
 
+// ------------------------------------------- generic column sweep (any K <= 32, any R)
+// Same three passes as k_cols_v1 for the shapes whose (R+1) x F x 8 tile does not fit in shared memory
+// next to the dictionary (K > 12, or the R = 30 chains of MCEM_M1).  The sample slots are read straight
+// from HBM in the H pass -- a warp covers 4 bins x 8 frames = 128 contiguous bytes of the column-tile
+// layout -- and from L2 in the g and cost passes (the tiles in flight on the chip stay far below its
+// capacity).  The rank-K part is taken out of the element loop: the H pass leaves a = X2 * s2 and s1 per
+// (f, n) in shared memory and a (k, n)-threaded product with the dictionary finishes the update, so no
+// thread carries K-sized arrays besides its column of H.  ~110 KB of shared memory: two CTAs per SM.
+struct GenArgs {
+  int F, K, KS, NP, R, ntiles;
+  const int32_t* frame_utt; const int32_t* frame_off;
+  const float* X2t; const float* Vs; const float* Mt;
+  float* Vb; float* g; float* H; const float* Wun; float* W; float* cost_part;
+};
+constexpr int GT = 256;
+__host__ __device__ inline size_t gen_smem_floats(int F, int KS, int K, int R) {
+  return (size_t)F * KS + (size_t)2 * F * NB + (size_t)(K + 1 + R) * NB + (size_t)K * NB + 32 + 8 * 2 * NB + 32 + 16;
+}
+
+template <int KMAX>
+__global__ void __launch_bounds__(GT, 2) k_cols_gen(GenArgs p) {
+  extern __shared__ __align__(16) float sg[];
+  const int F = p.F, K = p.K, KS = p.KS, NP = p.NP, R = p.R, MR = K + 1 + R, T8 = NP / NB;
+  float* W_s = sg;                                          // [F][KS]
+  float* a_s = W_s + (size_t)F * KS;                        // [F][NB]  X2 * s2 of the H pass
+  float* s1_s = a_s + (size_t)F * NB;                       // [F][NB]
+  float* meta = s1_s + (size_t)F * NB;                      // H_old [K][NB] | g [NB] | multiplicities [R][NB]
+  float* Hn_s = meta + (size_t)MR * NB;                     // [K][NB]
+  float* cn_s = Hn_s + (size_t)K * NB;                      // [32]
+  float* red = cn_s + 32;                                   // [8 warps][2][NB]
+  float* misc = red + 8 * 2 * NB;                           // [32]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n = tid & (NB - 1), fl = tid >> 3;              // 32 frequency lanes
+  const size_t slab = (size_t)T8 * F * NB;                  // one sample slot
+  int cur_b = -1, cur_fo = -1;
+  for (int t = p.ntiles - 1 - (int)blockIdx.x; t >= 0; t -= gridDim.x) {
+    const int b = p.frame_utt[(size_t)t * NB];
+    if (b < 0) { if (tid == 0) p.cost_part[t] = 0.f; continue; }
+    __syncthreads();                                        // previous tile is done with the shared arrays
+    for (int i = tid; i < MR * NB; i += GT) meta[i] = __ldg(p.Mt + (size_t)t * MR * NB + i);
+    if (b != cur_b) {
+      cur_b = b;
+      cur_fo = p.frame_off[b];
+      const float* wsrc = p.Wun + (size_t)b * F * K;
+      for (int i = tid; i < F * K; i += GT) { const int ff = i / K; W_s[ff * KS + (i - ff * K)] = __ldg(wsrc + i); }
+      if (KS > K) for (int i = tid; i < F * (KS - K); i += GT) { const int ff = i / (KS - K); W_s[ff * KS + K + (i - ff * (KS - K))] = 0.f; }
+      __syncthreads();
+      for (int k = warp; k < K; k += GT / 32) {             // c_k = sum_f |W_fk|  (mcem.py:128)
+        float sum = 0.f;
+        for (int ff = lane; ff < F; ff += 32) sum += fabsf(W_s[ff * KS + k]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if (lane == 0) cn_s[k] = sum;
+      }
+    }
+    __syncthreads();
+    if (t * NB == cur_fo) {                                 // the first tile of an utterance writes W / c (mcem.py:131)
+      float* wdst = p.W + (size_t)b * F * K;
+      for (int i = tid; i < F * K; i += GT) { const int ff = i / K, k = i - ff * K; wdst[i] = W_s[ff * KS + k] / cn_s[k]; }
+    }
+    const bool valid = p.frame_utt[(size_t)t * NB + n] >= 0;
+    const float gg = meta[K * NB + n];
+    const float* wts = meta + (K + 1) * NB + n;
+    const float* vs0 = p.Vs + (size_t)t * F * NB + n;       // + f*NB + r*slab
+    const float* x2p = p.X2t + (size_t)t * F * NB + n;
+    float hk[KMAX];
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) hk[k] = (k < K) ? meta[k * NB + n] : 0.f;
+    auto dot_w = [&](const float* wrow, const float (&h)[KMAX]) -> float {
+      float vb0 = 0.f, vb1 = 0.f;
+#pragma unroll
+      for (int k4 = 0; k4 < KMAX; k4 += 4) {
+        const float4 t4 = *reinterpret_cast<const float4*>(wrow + k4);
+        vb0 = fmaf(t4.x, h[k4], fmaf(t4.z, h[k4 + 2], vb0));
+        vb1 = fmaf(t4.y, h[k4 + 1], fmaf(t4.w, h[k4 + 3], vb1));
+      }
+      return vb0 + vb1;
+    };
+
+    // ---------------- pass A: s1, s2 with Vb = Wun @ H_old (mcem.py:113-121)
+    for (int f = fl; f < F; f += 32) {
+      const float vb = dot_w(W_s + f * KS, hk);
+      const float* vs = vs0 + (size_t)f * NB;
+      float s1 = 0.f, s2 = 0.f;
+      int r = 0;
+      for (; r + 1 < R; r += 2) pair_acc(gg, vb, __ldg(vs + r * slab), __ldg(vs + (r + 1) * slab), wts[r * NB], wts[(r + 1) * NB], s1, s2);
+      if (r < R) single_acc(gg, vb, __ldg(vs + r * slab), wts[r * NB], s1, s2);
+      a_s[f * NB + n] = __ldg(x2p + (size_t)f * NB) * s2;
+      s1_s[f * NB + n] = s1;
+    }
+    __syncthreads();
+    // H update: thread (k, n) finishes  H <- H * sqrt( (W^T (X2 s2)) / (W^T s1) )
+    if (tid < K * NB) {
+      const int k = tid >> 3;
+      float nu0 = 0.f, nu1 = 0.f, de0 = 0.f, de1 = 0.f;
+      int f = 0;
+      for (; f + 1 < F; f += 2) {
+        const float w0 = W_s[f * KS + k], w1 = W_s[(f + 1) * KS + k];
+        nu0 = fmaf(w0, a_s[f * NB + n], nu0); de0 = fmaf(w0, s1_s[f * NB + n], de0);
+        nu1 = fmaf(w1, a_s[(f + 1) * NB + n], nu1); de1 = fmaf(w1, s1_s[(f + 1) * NB + n], de1);
+      }
+      if (f < F) { const float w0 = W_s[f * KS + k]; nu0 = fmaf(w0, a_s[f * NB + n], nu0); de0 = fmaf(w0, s1_s[f * NB + n], de0); }
+      Hn_s[tid] = meta[tid] * sqrtf((nu0 + nu1) / (de0 + de1));
+    }
+    __syncthreads();
+    float hn[KMAX];
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) hn[k] = (k < K) ? Hn_s[k * NB + n] : 0.f;
+
+    // ---------------- pass B: Vb = Wun @ H_new (mcem.py:124), g update (:138-142)
+    float ng = 0.f, dg = 0.f;
+    for (int f = fl; f < F; f += 32) {
+      const float vb = dot_w(W_s + f * KS, hn);
+      if (valid) p.Vb[(size_t)f * NP + (size_t)t * NB + n] = vb;
+      a_s[f * NB + n] = vb;                                 // kept for the cost pass
+      const float* vs = vs0 + (size_t)f * NB;
+      float t1 = 0.f, t2 = 0.f;
+      int r = 0;
+      for (; r + 1 < R; r += 2) {
+        const float va = __ldg(vs + r * slab), vc = __ldg(vs + (r + 1) * slab);
+        const float a = fmaf(gg, va, vb), c = fmaf(gg, vc, vb);
+        const float ip = rcp_fast(a * c);
+        const float ia = c * ip, ic = a * ip;
+        const float ua = wts[r * NB] * va * ia, uc = wts[(r + 1) * NB] * vc * ic;
+        t1 += ua + uc;
+        t2 = fmaf(ua, ia, fmaf(uc, ic, t2));
+      }
+      if (r < R) {
+        const float va = __ldg(vs + r * slab);
+        const float ia = rcp_fast(fmaf(gg, va, vb)), ua = wts[r * NB] * va * ia;
+        t1 += ua;
+        t2 = fmaf(ua, ia, t2);
+      }
+      ng = fmaf(__ldg(x2p + (size_t)f * NB), t2, ng);
+      dg += t1;
+    }
+    ng += __shfl_xor_sync(0xffffffffu, ng, 8);
+    ng += __shfl_xor_sync(0xffffffffu, ng, 16);
+    dg += __shfl_xor_sync(0xffffffffu, dg, 8);
+    dg += __shfl_xor_sync(0xffffffffu, dg, 16);
+    if (lane < NB) { red[(warp * 2) * NB + lane] = ng; red[(warp * 2 + 1) * NB + lane] = dg; }
+    __syncthreads();
+    float sn = 0.f, sd = 0.f;
+#pragma unroll
+    for (int w8 = 0; w8 < 8; ++w8) { sn += red[(w8 * 2) * NB + n]; sd += red[(w8 * 2 + 1) * NB + n]; }
+    const float gnew = gg * sqrtf(sn / sd);
+    if (tid < NB && valid) p.g[(size_t)t * NB + n] = gnew;
+    if (tid < K * NB && valid) p.H[(size_t)(tid >> 3) * NP + (size_t)t * NB + n] = Hn_s[tid] * cn_s[tid >> 3];   // mcem.py:133
+
+    // ---------------- pass C: cost with the new g (mcem.py:151-152, :68-70)
+    float cl = 0.f, cr = 0.f;
+    for (int f = fl; f < F; f += 32) {
+      const float vb = a_s[f * NB + n];
+      const float* vs = vs0 + (size_t)f * NB;
+      float sl = 0.f, sr = 0.f;
+      int r = 0;
+      for (; r + 1 < R; r += 2) {
+        const float a = fmaf(gnew, __ldg(vs + r * slab), vb), c = fmaf(gnew, __ldg(vs + (r + 1) * slab), vb);
+        const float wa = wts[r * NB], wc = wts[(r + 1) * NB];
+        sl = fmaf(wa, lg2_fast(a), fmaf(wc, lg2_fast(c), sl));
+        sr = fmaf(fmaf(wa, c, wc * a), rcp_fast(a * c), sr);
+      }
+      if (r < R) {
+        const float a = fmaf(gnew, __ldg(vs + r * slab), vb), wa = wts[r * NB];
+        sl = fmaf(wa, lg2_fast(a), sl);
+        sr = fmaf(wa, rcp_fast(a), sr);
+      }
+      cl += sl;
+      cr = fmaf(__ldg(x2p + (size_t)f * NB), sr, cr);
+    }
+    float cs = valid ? fmaf(cl, 0.6931471805599453f, cr) : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cs += __shfl_xor_sync(0xffffffffu, cs, o);
+    if (lane == 0) misc[warp] = cs;
+    __syncthreads();
+    if (tid == 0) {
+      float sum = 0.f;
+      for (int w8 = 0; w8 < 8; ++w8) sum += misc[w8];
+      p.cost_part[t] = sum;
+    }
+  }
+}
+
+template <int KMAX>
+int32_t launch_cols_gen(const GenArgs& a, size_t smem, int grid, cudaStream_t st) {
+  static size_t smem_set = 0;
+  if (smem_set != smem) {
+    cudaError_t e = cudaFuncSetAttribute(k_cols_gen<KMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(GVN_E_CUDA, "k_cols_gen smem attr (%zu B): %s", smem, cudaGetErrorString(e));
+    smem_set = smem;
+  }
+  k_cols_gen<KMAX><<<grid, GT, smem, st>>>(a);
+  return check_launch("k_cols_gen");
+}
+
 template <int KMAX, int RT>
 int32_t launch_cols(const ColsArgs& a, size_t smem, int grid, cudaStream_t st) {
   static size_t smem_set = 0;
@@ -632,7 +827,12 @@ int32_t launch_cols(const ColsArgs& a, size_t smem, int grid, cudaStream_t st) {
 
 template <int KMAX, int RT>
 int32_t launch_w(const gvn_batch* b, int R, const float* Mt, cudaStream_t st) {
-  const size_t smem = (size_t)WS * w_stage_floats(b->K, R) * 4;
+  const size_t stage = (size_t)w_stage_floats(b->K, R) * 4;
+  const size_t budget = (KMAX > 16 || 2 * stage > 100 * 1024 ? 200 : 100) * 1024;    // one or two CTAs per SM
+  int ws = (int)(budget / stage);
+  if (ws > WS) ws = WS;
+  if (ws < 2) return fail(GVN_E_UNSUPPORTED_SHAPE, "M-step W sweep: a ring stage of %zu bytes does not fit (R=%d)", stage, R);
+  const size_t smem = (size_t)ws * stage;
   static size_t smem_set = 0;
   if (smem_set != smem) {
     cudaError_t e = cudaFuncSetAttribute(k_w_v2<KMAX, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -640,7 +840,7 @@ int32_t launch_w(const gvn_batch* b, int R, const float* Mt, cudaStream_t st) {
     smem_set = smem;
   }
   dim3 gw((b->F + WROWS - 1) / WROWS, b->B);
-  k_w_v2<KMAX, RT><<<gw, WT, smem, st>>>(b->F, b->K, b->NP, R, b->frame_off, b->n_frames, b->X2t, b->Vs, Mt, b->W, b->Wun);
+  k_w_v2<KMAX, RT><<<gw, WT, smem, st>>>(b->F, b->K, b->NP, R, ws, b->frame_off, b->n_frames, b->X2t, b->Vs, Mt, b->W, b->Wun);
   return check_launch("k_w_v2");
 }
 
@@ -656,43 +856,67 @@ int32_t launch_v1_k(const gvn_batch* b, int R, const ColsArgs& a, size_t smem, i
 
 }  // namespace
 
-// true when variant 1 can run this shape (the tile block must fit in shared memory)
+inline int kmax_gen(int K) { return K <= 16 ? 16 : 32; }
+inline int ks_gen(int K) { return kmax_gen(K) + 4; }     // dictionary row stride of the generic sweep: float4 reads cover KMAX columns
+
+// variant 1 proper: the tile block fits in shared memory next to the dictionary
+static bool v1_staged(const gvn_batch* b, int R) {
+  if (b->K > 16) return false;
+  return cols_smem_floats(b->F, ks_of(b->K), b->K, R, kmax_of(b->K)) * 4 <= 227 * 1024 &&
+         (size_t)2 * w_stage_floats(b->K, R) * 4 <= 100 * 1024;
+}
+
+// true when the bulk-copy W sweep + one of the two column sweeps can run this shape
 bool mstep_v1_supported(const gvn_batch* b, int R) {
-  if (b->K > 16 || b->X2t == nullptr) return false;
-  const size_t bytes = cols_smem_floats(b->F, ks_of(b->K), b->K, R, kmax_of(b->K)) * 4;
-  const size_t wbytes = (size_t)WS * w_stage_floats(b->K, R) * 4;
-  return bytes <= 227 * 1024 && wbytes <= 227 * 1024;
+  if (b->X2t == nullptr || b->K > 32) return false;
+  if (v1_staged(b, R)) return true;
+  const size_t wstage = (size_t)w_stage_floats(b->K, R) * 4;
+  return 2 * wstage <= 200 * 1024 && gen_smem_floats(b->F, ks_gen(b->K), b->K, R) * 4 <= 227 * 1024;
 }
 
 // workspace of variant 1: the column data in tile order
 size_t mstep_v1_workspace_bytes(const gvn_batch* b) { return (size_t)(b->K + 1 + b->R_cap) * b->NP * sizeof(float); }
 
 int32_t launch_mstep_v1(const gvn_batch* b, int R, float* cost_part, float* Mt, cudaStream_t st) {
-  const int KMAX = kmax_of(b->K);
   k_tile_meta<<<148, 256, 0, st>>>(b->K, R, b->NP, b->H, b->g, b->Vs_w, Mt);
   int32_t rc = check_launch("k_tile_meta");
   if (rc) return rc;
-  ColsArgs a;
-  a.F = b->F; a.K = b->K; a.KS = ks_of(b->K); a.NP = b->NP; a.R = R; a.B = b->B;
-  a.ntiles = b->NP / NB;
-  const int NI = (b->F + CFL - 1) / CFL;
-  a.nchunk = NI < MAXCH ? NI : MAXCH;
-  a.frame_utt = b->frame_utt; a.frame_off = b->frame_off; a.X2t = b->X2t; a.Vs = b->Vs; a.Mt = Mt;
-  a.Vb = b->Vb; a.g = b->g; a.H = b->H; a.Wun = b->Wun; a.W = b->W; a.cost_part = cost_part;
-  const size_t smem = cols_smem_floats(b->F, a.KS, b->K, R, KMAX) * 4;
   static int sms = 0;
   if (sms == 0) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   }
-  const int grid = a.ntiles < sms ? a.ntiles : sms;
-  switch (KMAX) {
-    case 4: return launch_v1_k<4>(b, R, a, smem, grid, st);
-    case 8: return launch_v1_k<8>(b, R, a, smem, grid, st);
-    case 12: return launch_v1_k<12>(b, R, a, smem, grid, st);
-    default: return launch_v1_k<16>(b, R, a, smem, grid, st);
+  const int ntiles = b->NP / NB;
+  if (v1_staged(b, R)) {
+    const int KMAX = kmax_of(b->K);
+    ColsArgs a;
+    a.F = b->F; a.K = b->K; a.KS = ks_of(b->K); a.NP = b->NP; a.R = R; a.B = b->B;
+    a.ntiles = ntiles;
+    const int NI = (b->F + CFL - 1) / CFL;
+    a.nchunk = NI < MAXCH ? NI : MAXCH;
+    a.frame_utt = b->frame_utt; a.frame_off = b->frame_off; a.X2t = b->X2t; a.Vs = b->Vs; a.Mt = Mt;
+    a.Vb = b->Vb; a.g = b->g; a.H = b->H; a.Wun = b->Wun; a.W = b->W; a.cost_part = cost_part;
+    const size_t smem = cols_smem_floats(b->F, a.KS, b->K, R, KMAX) * 4;
+    const int grid = a.ntiles < sms ? a.ntiles : sms;
+    switch (KMAX) {
+      case 4: return launch_v1_k<4>(b, R, a, smem, grid, st);
+      case 8: return launch_v1_k<8>(b, R, a, smem, grid, st);
+      case 12: return launch_v1_k<12>(b, R, a, smem, grid, st);
+      default: return launch_v1_k<16>(b, R, a, smem, grid, st);
+    }
   }
+  // generic shapes: bulk-copy W sweep (runtime R) + L2-resident column sweep
+  rc = b->K <= 16 ? launch_w<16, 0>(b, R, Mt, st) : launch_w<32, 0>(b, R, Mt, st);
+  if (rc) return rc;
+  GenArgs a;
+  a.F = b->F; a.K = b->K; a.KS = ks_gen(b->K); a.NP = b->NP; a.R = R; a.ntiles = ntiles;
+  a.frame_utt = b->frame_utt; a.frame_off = b->frame_off; a.X2t = b->X2t; a.Vs = b->Vs; a.Mt = Mt;
+  a.Vb = b->Vb; a.g = b->g; a.H = b->H; a.Wun = b->Wun; a.W = b->W; a.cost_part = cost_part;
+  const size_t smem = gen_smem_floats(b->F, a.KS, b->K, R) * 4;
+  const int per_sm = smem <= 110 * 1024 ? 2 : 1;
+  const int grid = ntiles < sms * per_sm ? ntiles : sms * per_sm;
+  return b->K <= 16 ? launch_cols_gen<16>(a, smem, grid, st) : launch_cols_gen<32>(a, smem, grid, st);
 }
 
 }  // namespace gvn

@@ -146,8 +146,10 @@ int32_t gvn_estep(const gvn_batch* batch /*HOST*/, const void* packed, int32_t b
 /* NMF / gain M-step: replaces EM.M_step + compute_expected_neg_log_like
  * (mcem.py:90-152, :68-70).  Updates W, H, g, Vb in place; cost_part receives one partial
  * sum per GVN_COST_TILE frames ([NP/8]); gvn_cost_reduce turns niter of them into cost[niter][B].
- * variant 0: straightforward schedule, any shape.  variant 1: HBM-bound schedule (column tiles
- * staged once in shared memory); falls back to 0 when the tile does not fit (K > 12 at R = 10). */
+ * variant 0: straightforward schedule, any shape (the schedule the parity tests pin to the oracle).
+ * variant 1 (default): bulk-copy W sweep + column sweep with the (R+1) x F x 8 tile staged once in
+ * shared memory (K <= 12 at R = 10), or the generic L2-resident column sweep (K <= 32, R <= ~90);
+ * falls back to 0 when neither fits. */
 size_t gvn_mstep_workspace_bytes(const gvn_batch* batch /*HOST*/);
 int32_t gvn_mstep(const gvn_batch* batch /*HOST*/, int32_t R, float* cost_part, void* workspace,
                   int32_t variant, void* stream);

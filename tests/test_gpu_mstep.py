@@ -32,7 +32,9 @@ def _random_batch(n_frames, F, K, L, R, seed):
 
 
 @pytest.mark.parametrize("n_frames,F,K,R", [([251, 100, 37, 256], 513, 10, 10), ([64], 513, 12, 9), ([40, 33], 257, 4, 3),
-                                            ([251] * 6, 513, 10, 10), ([70], 129, 1, 2)])
+                                            ([251] * 6, 513, 10, 10), ([70], 129, 1, 2),
+                                            # shapes of the generic column sweep: K = 32 (config 4), R = 30 (MCEM_M1's E chain), odd sizes
+                                            ([251, 90], 513, 32, 10), ([251], 513, 10, 30), ([100, 37], 257, 20, 5), ([64], 513, 16, 10)])
 def test_mstep_v1_matches_v0(n_frames, F, K, R):
     from gvn import engine as E
     out = {}
@@ -52,10 +54,10 @@ def test_mstep_v1_matches_v0(n_frames, F, K, R):
     np.testing.assert_allclose(np.abs(out[1]["W"]).sum(1), 1.0, rtol=1e-5)          # mcem.py:128-131
 
 
-def test_mstep_v1_falls_back_when_tile_does_not_fit():
+def test_mstep_v1_falls_back_when_nothing_fits():
     from gvn import engine as E
-    b = _random_batch([64], 513, 32, 16, 10, seed=1)                                 # K=32: variant 0 runs
+    b = _random_batch([64], 513, 10, 16, 120, seed=1)                                # R=120: no ring stage fits, variant 0 runs
     sc = E.MstepScratch(b, 1)
-    E.mstep(b, 10, sc, 0, 1)
+    E.mstep(b, 120, sc, 0, 1)
     torch.cuda.synchronize()
     assert bool(torch.isfinite(b.W).all())

@@ -35,4 +35,4 @@ print("C3  M2-VAD, labels from the classifier on the device, 64 utterances x 4 s
 x, s, n = synth_batch(8, seed=0, T=480000)
 cfg = McemConfig(model="M1", niter=100, nmf_rank=32, burnin_E_step=10, precision="f16")
 t = timeit(Enhancer(m1, cfg, "cuda:0"), list(x), reps=2)
-print("C4  M1, 8 utterances x 30 s (N=1876), K=32, R_E=10, niter=100, f16 (M-step variant 0 fallback for K=32): %.1f ms per batch (%.2f utt/s)" % (t * 1e3, 8 / t))
+print("C4  M1, 8 utterances x 30 s (N=1876), K=32, R_E=10, niter=100, f16 (generic column sweep for K=32): %.1f ms per batch (%.2f utt/s)" % (t * 1e3, 8 / t))
