@@ -238,10 +238,13 @@ def main():
     if rank == 0:
         clocks.start()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.profiler.start()                             # `ncu --profile-from-start off` sees the timed region only
     t0.record()
     for i in range(args.steps):
         s_hat, n_hat, cost, b, rows = device_step(up, refs, timers=timers, seed=100 + i)
     t1.record()
+    torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
     barrier()
     launches = int(lib.gvn_launch_count()) - launches0      # kernels of libgvn.so launched inside the timed region
     clk = clocks.stop() if rank == 0 else None

@@ -17,6 +17,8 @@
 // reference is a multiplicity-weighted sum over the R slots.
 // Transcendental budget: 1/a and 1/c of a pair of slots come from ONE reciprocal of the product
 // (1/a = c * rcp(ac)); Vx >= K*eps^2 ~ 1e-15, so the product stays far inside the fp32 range.
+#include <stdlib.h>
+
 #include "gvn_common.cuh"
 
 namespace gvn {
@@ -888,7 +890,9 @@ int32_t launch_mstep_v1(const gvn_batch* b, int R, float* cost_part, float* Mt, 
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   }
   const int ntiles = b->NP / NB;
-  if (v1_staged(b, R)) {
+  static int force_gen = -1;                            // GVN_MSTEP_GEN=1: take the generic column sweep everywhere (experiments)
+  if (force_gen < 0) { const char* e = getenv("GVN_MSTEP_GEN"); force_gen = e ? atoi(e) : 0; }
+  if (v1_staged(b, R) && !force_gen) {
     const int KMAX = kmax_of(b->K);
     ColsArgs a;
     a.F = b->F; a.K = b->K; a.KS = ks_of(b->K); a.NP = b->NP; a.R = R; a.B = b->B;
