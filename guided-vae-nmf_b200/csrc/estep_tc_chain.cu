@@ -164,7 +164,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_estep_tc(const __grid_constant_
   uint64_t* bar_free = bars + 5;                          // [2] E -> M : accumulator buffer drained
   uint64_t* bar_full = bars + 7;                          // [nstage] TMA -> E
   uint64_t* bar_empty = bars + 7 + MAX_STAGES;            // [nstage] E -> P
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7 + 2 * MAX_STAGES);
+  uint64_t* bar_eps = bars + 7 + 2 * MAX_STAGES;          // E(owners) -> E(noise warps): hand-over buffer has been read
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8 + 2 * MAX_STAGES);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n0 = blockIdx.x * TM;
@@ -186,6 +187,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_estep_tc(const __grid_constant_
     mbar_init(bar_z, 4);
     mbar_init(bar_h, NEW);
     mbar_init(bar_hfull, 1);
+    mbar_init(bar_eps, 4);
     for (int i = 0; i < 2; ++i) { mbar_init(bar_d + i, 1); mbar_init(bar_free + i, NEW); }
     for (int i = 0; i < p.nstage; ++i) { mbar_init(bar_full + i, 1); mbar_init(bar_empty + i, NEW); }
     mbar_init_fence();
@@ -327,6 +329,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_estep_tc(const __grid_constant_
       uint32_t w[16];
 #pragma unroll
       for (int l = 0; l < 16; ++l) w[l] = __float_as_uint(e[l % L16]);
+      // buffer (m & 1) held the noise of step m-2; the owners signal when they have read it for the last time
+      // (long before this point: the draw above takes thousands of cycles, their read a few hundred)
+      if (m >= 2) mbar_wait(bar_eps, (uint32_t)(m - 2) & 1);
       __syncwarp();
       tmem_st16(tlane + COL_EPS + 16 * (m & 1), w);
       tmem_st1(tlane + COL_LOGU + (m & 1), __float_as_uint(draw_logu(m)));
@@ -559,6 +564,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_estep_tc(const __grid_constant_
           __syncwarp();
           tmem_ld16(tlane + COL_EPS + 16 * (m & 1), w);
           tmem_ld_wait();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_eps);              // phase m: buffer (m & 1) may be overwritten
           if (ok) {
 #pragma unroll
             for (int l = 0; l < L16; ++l) z[l] = fmaf(p.sd, __uint_as_float(w[l % 16]), z[l]);
@@ -638,7 +645,7 @@ int32_t make_tile_map(CUtensorMap* m, const uint32_t* base, int F, int NP) {
 template <int L16, bool PROF_ON, int VAR>
 int32_t launch_tc(const CUtensorMap& mx, const TcArgs& a, int grid, cudaStream_t st) {
   const size_t fixed = (size_t)HID * 2 * L16 * 2 + (size_t)HID * HID * 2 + (size_t)a.FN * HID * 2 + (size_t)(a.FN + 16 + HID) * 4 +
-                       (size_t)2 * NE * 8 + (7 + 2 * MAX_STAGES) * 8 + 16;
+                       (size_t)2 * NE * 8 + (8 + 2 * MAX_STAGES) * 8 + 16;
   TcArgs args = a;
   const size_t cap = 227 * 1024;
   int nstage = (int)((cap - fixed) / STAGE_BYTES);
