@@ -93,37 +93,26 @@ __device__ __forceinline__ uint32_t tanh_f16x2(float lo, float hi) {
   return y;
 }
 
-// 2^t on the FMA/ALU pipes (Cody-Waite split + degree-6 minimax, ~1e-7 relative): takes MUFU.EX2
-// work off the special-function pipe, which bounds the chain epilogue
-__device__ __forceinline__ float ex2_poly(float t) {
-  t = fmaxf(t, -125.f);
-  const float j = t + 12582912.f;                        // 1.5 * 2^23: round(t) lands in the low mantissa bits
-  const float f = t - (j - 12582912.f);                  // in [-0.5, 0.5]
-  float q = 1.535336188319500e-4f;
-  q = fmaf(q, f, 1.339887440266574e-3f);
-  q = fmaf(q, f, 9.618437357674640e-3f);
-  q = fmaf(q, f, 5.550332471162809e-2f);
-  q = fmaf(q, f, 2.402264791363012e-1f);
-  q = fmaf(q, f, 6.931472028550421e-1f);
-  q = fmaf(q, f, 1.0f);
-  return __int_as_float(__float_as_int(q) + (__float_as_int(j) << 23));
-}
-
 __device__ __forceinline__ void st_stream(float* p, float v) { asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
 
 __device__ __forceinline__ void bar_epilogue() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-// XV[f][n] = bf16(X2) << 16 | bf16(Vb)
+// XV[f][n]: low half = bf16(Vb); high half chosen so that the WHOLE word, read as an f32, is the value nearest to
+// X2 (the low half then acts as extra mantissa bits of X2: same 2^-9 relative bound as a bf16 rounding, and the
+// epilogue needs no mask to take X2 out of the word)
+__device__ __forceinline__ uint32_t pack_xv_word(float x2, float vb) {
+  const __nv_bfloat16 vbb = __float2bfloat16_rn(vb);
+  const uint32_t lo = (uint32_t)(*reinterpret_cast<const unsigned short*>(&vbb));
+  const uint32_t xb = __float_as_uint(fmaxf(x2, 0.f));
+  const uint32_t hi = xb > lo ? (xb - lo + 0x8000u) >> 16 : 0u;
+  return (hi << 16) | lo;
+}
 __global__ void __launch_bounds__(256) k_pack_xv(size_t n4, const float4* __restrict__ X2, const float4* __restrict__ Vb,
                                                  uint4* __restrict__ XV) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
     const float4 x = X2[i], v = Vb[i];
     uint4 o;
-    __nv_bfloat162 t;
-    t = __floats2bfloat162_rn(v.x, x.x); o.x = *reinterpret_cast<uint32_t*>(&t);
-    t = __floats2bfloat162_rn(v.y, x.y); o.y = *reinterpret_cast<uint32_t*>(&t);
-    t = __floats2bfloat162_rn(v.z, x.z); o.z = *reinterpret_cast<uint32_t*>(&t);
-    t = __floats2bfloat162_rn(v.w, x.w); o.w = *reinterpret_cast<uint32_t*>(&t);
+    o.x = pack_xv_word(x.x, v.x); o.y = pack_xv_word(x.y, v.y); o.z = pack_xv_word(x.z, v.z); o.w = pack_xv_word(x.w, v.w);
     XV[i] = o;
   }
 }
@@ -414,7 +403,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_estep_tc(const __grid_constant_
         constexpr bool V_PF = (VAR & 1) != 0;             // prefetch the next stage's accumulator columns
         constexpr bool V_PRE = false;
         constexpr bool V_PROBE = (VAR & 2) != 0;          // probe the next stage's ring barrier before this stage's math
-        constexpr bool V_POLY = (VAR & 4) != 0;           // every second exp on the FMA pipe
+        constexpr bool V_PACK = (VAR & 4) != 0;           // packed f32x2 arithmetic in the pair loop
         auto stage = [&](uint32_t (&r)[16], uint32_t (&rn)[16], int s_) {
           const int f0 = c * 128 + s_ * SROWS + 16 * half;
           const uint32_t* xv = nullptr;
@@ -446,20 +435,40 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_estep_tc(const __grid_constant_
               asm volatile("" ::: "memory");
             }
             if (!V_PF) tmem_ld_wait();
+            if (V_PACK) {                                  // packed f32x2 arithmetic (FFMA2) where two bins run in lock step
+              float2 acc2 = make_float2(sl, sr);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float2 t = __ffma2_rn(make_float2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1])), make_float2(SC3, SC3),
+                                            make_float2(b3v[2 * j], b3v[2 * j + 1]));
+                const float v0 = ex2_approx(t.x), v1 = ex2_approx(t.y);
+                if (ENERGY) {
+                  const uint32_t w0 = V_PRE ? wv[2 * j] : xv[(2 * j) * TM], w1 = V_PRE ? wv[2 * j + 1] : xv[(2 * j + 1) * TM];
+                  const float2 ab = __ffma2_rn(make_float2(g, g), make_float2(v0, v1),
+                                               make_float2(__uint_as_float(w0 << 16), __uint_as_float(w1 << 16)));
+                  const float pr = ab.x * ab.y;
+                  const float qn = fmaf(__uint_as_float(w0), ab.y, __uint_as_float(w1) * ab.x);
+                  acc2 = __ffma2_rn(make_float2(1.0f, qn), make_float2(lg2_approx(pr), rcp_approx(pr)), acc2);
+                }
+                if (STORE && valid) { st_stream(vo + (2 * j) * 8, v0); st_stream(vo + (2 * j + 1) * 8, v1); }
+              }
+              sl = acc2.x; sr = acc2.y;
+            } else {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const float t0 = fmaf(__uint_as_float(r[2 * j]), SC3, b3v[2 * j]), t1 = fmaf(__uint_as_float(r[2 * j + 1]), SC3, b3v[2 * j + 1]);
               const float v0 = ex2_approx(t0);
-              const float v1 = V_POLY ? ex2_poly(t1) : ex2_approx(t1);
+              const float v1 = ex2_approx(t1);
               if (ENERGY) {
                 const uint32_t w0 = V_PRE ? wv[2 * j] : xv[(2 * j) * TM], w1 = V_PRE ? wv[2 * j + 1] : xv[(2 * j + 1) * TM];
                 const float a = fmaf(g, v0, __uint_as_float(w0 << 16)), b = fmaf(g, v1, __uint_as_float(w1 << 16));
                 const float pr = a * b;
                 sl += lg2_approx(pr);
-                const float qn = fmaf(__uint_as_float(w0 & 0xffff0000u), b, __uint_as_float(w1 & 0xffff0000u) * a);
+                const float qn = fmaf(__uint_as_float(w0), b, __uint_as_float(w1) * a);      // X2 = the whole word (k_pack_xv)
                 sr = fmaf(qn, rcp_approx(pr), sr);
               }
               if (STORE && valid) { st_stream(vo + (2 * j) * 8, v0); st_stream(vo + (2 * j + 1) * 8, v1); }
+            }
             }
           } else {                                         // ragged tail of the spectrum (F = 513: one bin)
             const int nv = F - f0;
@@ -472,7 +481,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_estep_tc(const __grid_constant_
                 const uint32_t w0 = xv[j * TM];
                 const float a = fmaf(g, v0, __uint_as_float(w0 << 16));
                 sl += lg2_approx(a);
-                sr = fmaf(__uint_as_float(w0 & 0xffff0000u), rcp_approx(a), sr);
+                sr = fmaf(__uint_as_float(w0), rcp_approx(a), sr);
               }
               if (STORE && valid) st_stream(vo + j * 8, v0);
             }

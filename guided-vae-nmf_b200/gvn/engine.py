@@ -77,9 +77,25 @@ class PackedDecoder:
         self._keep = w
 
 
+_PARAMS = {}
+
+
+def _device_param(p, device):
+    """Device f32 copy of a module parameter, made once per (parameter, in-place version): a pageable
+    host-to-device copy per call would order the host behind the whole stream (see const_i32)."""
+    if p.device == torch.device(device) and p.dtype == torch.float32:
+        return p.detach().contiguous()
+    key = (id(p), str(device))
+    hit = _PARAMS.get(key)
+    if hit is None or hit[0] is not p or hit[1] != p._version:
+        if len(_PARAMS) >= 256:
+            _PARAMS.clear()
+        hit = _PARAMS[key] = (p, p._version, p.detach().to(device=device, dtype=torch.float32).contiguous())
+    return hit[2]
+
+
 def _linear_params(layer, device):
-    return (layer.weight.detach().to(device=device, dtype=torch.float32).contiguous(),
-            layer.bias.detach().to(device=device, dtype=torch.float32).contiguous())
+    return _device_param(layer.weight, device), _device_param(layer.bias, device)
 
 
 def dense(W, b, in0, in1, act, NP, mean=None, std=None, eps=0.0):
@@ -222,6 +238,23 @@ def device_buffer(tag, shape, dtype, device):
     return buf
 
 
+_CONST_I32 = {}
+
+
+def const_i32(values, device):
+    """Small read-only int32 vector on the device (lengths, paddings), created once per distinct content.
+    A fresh ``torch.tensor(list, device=...)`` is a pageable host-to-device copy, which the CUDA runtime
+    orders behind ALL work already queued on the stream: placed after the EM loop it stalls the host for
+    the whole enhancement and nothing can be prepared for the next batch meanwhile."""
+    key = (tuple(int(v) for v in values), str(device))
+    t = _CONST_I32.get(key)
+    if t is None:
+        if len(_CONST_I32) >= 256:
+            _CONST_I32.clear()
+        t = _CONST_I32[key] = torch.tensor(list(key[0]), dtype=torch.int32, device=device)
+    return t
+
+
 def upload_waveforms(wavs, device, pinned=None, tag="wav"):
     """Packs B waveforms into one zero-padded (B, T_stride) f32 tensor on the device (pinned staging
     buffer and device buffer named by `tag`, so that two uploads can be in flight with two tags)."""
@@ -247,9 +280,8 @@ def download(t, tag):
 
 def stft_into(batch, wav_dev, T, T_stride, n_fft, hop, end_pad):
     lib = _lib.load()
-    i32 = dict(dtype=torch.int32, device=batch.device)
-    T_d = torch.tensor(T, **i32)
-    ep_d = torch.tensor([int(e) for e in end_pad], **i32)
+    T_d = const_i32(T, batch.device)
+    ep_d = const_i32(end_pad, batch.device)
     if min(T) <= n_fft // 2:
         raise _lib.GvnError(_lib.E_INVALID, "signal shorter than n_fft/2 cannot be reflect-padded")
     check(lib.gvn_stft_power(batch.struct(), _ptr(wav_dev), T_stride, _ptr(T_d), _ptr(ep_d), n_fft, hop, _stream()))
@@ -259,7 +291,7 @@ def stft_into(batch, wav_dev, T, T_stride, n_fft, hop, end_pad):
 def istft_from(batch, S, out_len, T_stride, n_fft, hop):
     """S: [F][NP][2] f32 on device -> (B, T_stride) f32 waveforms on device."""
     lib = _lib.load()
-    ol = torch.tensor([int(v) for v in out_len], dtype=torch.int32, device=batch.device)
+    ol = const_i32(out_len, batch.device)
     out = torch.empty(batch.B, T_stride, dtype=torch.float32, device=batch.device)
     ws = torch.empty(lib.gvn_istft_workspace_bytes(batch.struct(), n_fft), dtype=torch.uint8, device=batch.device)
     check(lib.gvn_istft(batch.struct(), _ptr(S), n_fft, hop, _ptr(ol), _ptr(out), T_stride, _ptr(ws), _stream()))
@@ -406,7 +438,7 @@ def energy_ratios(est, s_ref, n_ref, T):
     lib = _lib.load()
     B, T_stride = est.shape
     assert s_ref.shape == est.shape and n_ref.shape == est.shape
-    Td = T if torch.is_tensor(T) else torch.tensor([int(v) for v in T], dtype=torch.int32, device=est.device)
+    Td = T if torch.is_tensor(T) else const_i32(T, est.device)
     out = torch.empty(B, 3, dtype=torch.float64, device=est.device)
     check(lib.gvn_energy_ratios(_ptr(est.contiguous()), _ptr(s_ref.contiguous()), _ptr(n_ref.contiguous()), B, T_stride,
                                 _ptr(Td), _ptr(out), _stream()))

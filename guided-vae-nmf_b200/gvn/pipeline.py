@@ -48,7 +48,10 @@ class Enhancer:
         self.cfg = cfg
         self.vae = vae
         self.classifier = classifier
-        self.mean, self.std = mean, std
+        # standardisation constants of the classifier input live on the device from the start (a host array
+        # here would mean a blocking pageable copy in every classify call)
+        to_dev = lambda a: None if a is None else torch.as_tensor(a, dtype=torch.float32).reshape(-1).to(self.device)
+        self.mean, self.std = to_dev(mean), to_dev(std)
         with torch.cuda.device(self.device):
             self.dec = E.PackedDecoder(vae, self.device)
         self._batches = {}          # batch state in HBM is allocated once per shape and reused (stream-ordered)
@@ -130,50 +133,76 @@ class Enhancer:
             n_hat = E.istft_from(b, Nn, b.T, b.T_stride, b.nfft, b.hop)
         return s_hat, n_hat, cost
 
-    def enhance_many(self, batches, seed=0):
+    def enhance_many(self, batches, seed=0, device_hook=None):
         """Pipelined end-to-end enhancement of a sequence of batches.  ``batches`` yields dicts with keys
         ``wavs``, optionally ``labels`` and ``refs`` (clean speech, noise: adds the quality metrics).
-        The host packing and H2D copy of batch i+1 run on a second stream while batch i is enhanced; results
-        come back in pinned host buffers (valid until the next iteration).  Yields dicts with ``s_hat``,
-        ``n_hat`` (B, T_stride) f32, ``cost`` (niter, B) f64, ``metrics`` (B, 3) f64 or None, ``T``, byte counts."""
+        Three things overlap: the GPU enhances batch i while the host packs batch i+1 into pinned memory and a
+        second stream copies it to the device, and the kernels of batch i+1 are queued behind those of batch i
+        before the host waits for the results of batch i -- the GPU never drains between batches.  Nothing in
+        the loop orders the host behind the compute stream except the wait for a finished batch.  Results come
+        back in pinned host buffers (two sets, valid until the next iteration).  Yields dicts with ``s_hat``,
+        ``n_hat`` (B, T_stride) f32, ``cost`` (niter, B) f64, ``metrics`` (B, 3) f64 or None, ``T``, byte counts.
+        ``device_hook(i, cost_dev, metrics_dev)`` is called right after the kernels of batch i have been
+        queued (e.g. to queue a collective on the result rows, in stream order, without touching the host copies)."""
         dev = self.device
         main = torch.cuda.current_stream(dev)
         copy = getattr(self, "_copy_stream", None)
         if copy is None:
             copy = self._copy_stream = torch.cuda.Stream(dev)
-        consumed = [None, None]                             # main-stream events: inputs of slot p have been read
+        consumed = [None, None]                             # main-stream events: device inputs of slot p have been read
+        copied = [None, None]                               # copy-stream events: pinned staging of slot p has been read
 
         def start_upload(item, slot):
+            if copied[slot] is not None:
+                copied[slot].synchronize()                  # the staging buffers are about to be overwritten by the host
             with torch.cuda.stream(copy):
                 if consumed[slot] is not None:
                     copy.wait_event(consumed[slot])
                 up = self.upload(item["wavs"], item.get("labels"), item.get("refs"), slot=slot)
                 ev = torch.cuda.Event()
                 ev.record(copy)
+            copied[slot] = ev
             return up, ev
+
+        def launch(up, ev, i):
+            slot = i & 1
+            main.wait_event(ev)
+            if up["y"] is not None:
+                up["y"].record_stream(main)                 # allocated on the copy stream, read on this one
+            b = self.prepare(None, None, seed=seed + i, uploaded=up)
+            s_hat, n_hat, cost = self.run(b, seed=seed + i)
+            metrics = metrics_dev = None
+            if "ref_s" in up:
+                metrics_dev = E.energy_ratios(s_hat, up["ref_s"], up["ref_n"], b.T)
+                metrics = E.download(metrics_dev, "metrics%d" % slot)
+            if device_hook is not None:
+                device_hook(i, cost, metrics_dev)
+            consumed[slot] = torch.cuda.Event()
+            consumed[slot].record(main)
+            out = dict(s_hat=E.download(s_hat, "s_hat%d" % slot), n_hat=E.download(n_hat, "n_hat%d" % slot),
+                       cost=E.download(cost, "cost%d" % slot), metrics=metrics, T=b.T, h2d_bytes=up["h2d_bytes"],
+                       d2h_bytes=(s_hat.numel() + n_hat.numel()) * 4 + cost.numel() * 8 + (0 if metrics is None else metrics.numel() * 8))
+            done = torch.cuda.Event()
+            done.record(main)
+            return out, done
 
         it = iter(batches)
         nxt = next(it, None)
         pending = start_upload(nxt, 0) if nxt is not None else None
+        in_flight = None                                    # (results, event) of the batch queued before the current one
         i = 0
         while pending is not None:
-            up, ev = pending
-            main.wait_event(ev)
-            b = self.prepare(None, None, seed=seed + i, uploaded=up)
-            consumed[i & 1] = torch.cuda.Event()
-            consumed[i & 1].record(main)
-            s_hat, n_hat, cost = self.run(b, seed=seed + i)
-            metrics = None
-            if "ref_s" in up:
-                metrics = E.download(E.energy_ratios(s_hat, up["ref_s"], up["ref_n"], b.T), "metrics")
-            out = dict(s_hat=E.download(s_hat, "s_hat"), n_hat=E.download(n_hat, "n_hat"), cost=E.download(cost, "cost"),
-                       metrics=metrics, T=b.T, h2d_bytes=up["h2d_bytes"],
-                       d2h_bytes=(s_hat.numel() + n_hat.numel()) * 4 + cost.numel() * 8 + (0 if metrics is None else metrics.numel() * 8))
-            nxt = next(it, None)                            # pack + copy the next batch while this one computes
+            cur = launch(pending[0], pending[1], i)         # queued behind the batch in flight
+            nxt = next(it, None)                            # pack + copy the next batch while the GPU works
             pending = start_upload(nxt, (i + 1) & 1) if nxt is not None else None
-            main.synchronize()
-            yield out
+            if in_flight is not None:
+                in_flight[1].synchronize()
+                yield in_flight[0]
+            in_flight = cur
             i += 1
+        if in_flight is not None:
+            in_flight[1].synchronize()
+            yield in_flight[0]
 
     def enhance(self, wavs, labels=None, seed=0):
         """Host waveforms in, host waveforms out (the end-to-end call)."""

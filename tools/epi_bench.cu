@@ -46,6 +46,19 @@ __global__ void k(float* out, long long* cyc, int iters) {
       const float qn = fmaf(__uint_as_float(w0 & 0xffff0000u), b, __uint_as_float(w1 & 0xffff0000u) * a);
       if (MODE != 1) sr = fmaf(qn, rcpa(pr), sr); else sr = fmaf(qn, pr, sr);
     }
+    if (MODE == 6) {   // diet: bias and scale folded into the MMA (t = accumulator), Vb taken unmasked from the word, X2 = w << 16
+      const unsigned* x = xv + 16 * half * 128 + row;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float v0 = ex2a(r[2 * j]), v1 = ex2a(r[2 * j + 1]);
+        const unsigned w0 = x[(2 * j) * 128], w1 = x[(2 * j + 1) * 128];
+        const float a = fmaf(g, v0, __uint_as_float(w0)), b = fmaf(g, v1, __uint_as_float(w1));
+        const float pr = a * b;
+        sl += lg2a(pr);
+        const float qn = fmaf(__uint_as_float(w0 << 16), b, __uint_as_float(w1 << 16) * a);
+        sr = fmaf(qn, rcpa(pr), sr);
+      }
+    }
     if (MODE == 4 || MODE == 5) {   // packed f32x2 arithmetic; MODE 5: x2 taken unmasked from the word
       const unsigned* x = xv + 16 * half * 128 + row;
       float2 acc2 = make_float2(sl, sr);
@@ -85,6 +98,6 @@ void run(const char* name, int threads) {
   cudaFree(out); cudaFree(cyc);
 }
 int main() {
-  for (int th : {128, 256, 512}) { run<0>("full (ex2+lg2+rcp)", th); run<3>("full, LDS.128 swizzled", th); run<4>("full, packed f32x2", th); run<5>("full, packed + unmasked x2", th); run<1>("ex2 only", th); run<2>("lg2+rcp only", th); }
+  for (int th : {128, 256, 384, 512}) { run<6>("diet (no bias fma, 1 unpack)", th); run<0>("full (ex2+lg2+rcp)", th); run<3>("full, LDS.128 swizzled", th); run<4>("full, packed f32x2", th); run<5>("full, packed + unmasked x2", th); run<1>("ex2 only", th); run<2>("lg2+rcp only", th); }
   return 0;
 }
