@@ -102,9 +102,10 @@ int32_t gvn_estep(const gvn_batch* batch, const void* packed, int32_t burnin, in
   GVN_REQUIRE(burnin >= 0 && R >= 1 && R <= batch->R_cap, GVN_E_INVALID, "burnin=%d R=%d R_cap=%d", burnin, R, batch->R_cap);
   GVN_REQUIRE((noise->eps == nullptr) == (noise->u == nullptr), GVN_E_INVALID, "eps and u must both be given or both NULL");
   GVN_REQUIRE(var_RW > 0.f, GVN_E_INVALID, "var_RW=%g", (double)var_RW);
-  if (precision == GVN_PREC_FP32)
+  const int32_t prec = precision & ~GVN_PREC_XV_CURRENT;
+  if (prec == GVN_PREC_FP32)
     return launch_estep_simt(batch, packed, burnin, R, var_RW, noise, trace, (cudaStream_t)stream);
-  if (precision == GVN_PREC_F16X3 || precision == GVN_PREC_F16)
+  if (prec == GVN_PREC_F16X3 || prec == GVN_PREC_F16)
     return launch_estep_tc(batch, packed, burnin, R, var_RW, noise, trace, precision, (cudaStream_t)stream);
   return fail(GVN_E_INVALID, "unknown precision %d", precision);
 }

@@ -97,16 +97,7 @@ __device__ __forceinline__ void st_stream(float* p, float v) { asm volatile("st.
 
 __device__ __forceinline__ void bar_epilogue() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-// XV[f][n]: low half = bf16(Vb); high half chosen so that the WHOLE word, read as an f32, is the value nearest to
-// X2 (the low half then acts as extra mantissa bits of X2: same 2^-9 relative bound as a bf16 rounding, and the
-// epilogue needs no mask to take X2 out of the word)
-__device__ __forceinline__ uint32_t pack_xv_word(float x2, float vb) {
-  const __nv_bfloat16 vbb = __float2bfloat16_rn(vb);
-  const uint32_t lo = (uint32_t)(*reinterpret_cast<const unsigned short*>(&vbb));
-  const uint32_t xb = __float_as_uint(fmaxf(x2, 0.f));
-  const uint32_t hi = xb > lo ? (xb - lo + 0x8000u) >> 16 : 0u;
-  return (hi << 16) | lo;
-}
+// XV[f][n] = pack_xv_word(X2, Vb) (gvn_common.cuh) for the whole batch: the chain's per-bin constants
 __global__ void __launch_bounds__(256) k_pack_xv(size_t n4, const float4* __restrict__ X2, const float4* __restrict__ Vb,
                                                  uint4* __restrict__ XV) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
@@ -679,6 +670,8 @@ void set_profile_buffer(void* p) { g_prof = reinterpret_cast<unsigned long long*
 
 int32_t launch_estep_tc(const gvn_batch* b, const void* packed, int burnin, int R, float var_RW, const gvn_noise* nz,
                         const gvn_trace* tr, int precision, cudaStream_t st) {
+  const bool xv_current = (precision & GVN_PREC_XV_CURRENT) != 0;
+  precision &= ~GVN_PREC_XV_CURRENT;
   if (precision != GVN_PREC_F16)
     return fail(GVN_E_UNSUPPORTED_SHAPE, "precision %d: the hi/lo-split tensor-core chain is not built yet", precision);
   GVN_REQUIRE(b->XV != nullptr && b->Vs_w != nullptr, GVN_E_INVALID, "batch.XV / batch.Vs_w is NULL");
@@ -686,11 +679,14 @@ int32_t launch_estep_tc(const gvn_batch* b, const void* packed, int burnin, int 
   TcLayout t = tc_layout(b->L, b->F);
   const unsigned char* base = reinterpret_cast<const unsigned char*>(packed);
   // per-launch constants of the chain: X2 and Vb as one bf16 pair per (f, frame)
-  const size_t n4 = (size_t)b->F * b->NP / 4;
-  k_pack_xv<<<148 * 8, 256, 0, st>>>(n4, reinterpret_cast<const float4*>(b->X2), reinterpret_cast<const float4*>(b->Vb),
-                                     reinterpret_cast<uint4*>(b->XV));
-  int32_t rc = check_launch("k_pack_xv");
-  if (rc) return rc;
+  // (skipped when the caller vouches that gvn_mstep, which refreshes XV next to Vb, was the last writer of Vb)
+  int32_t rc = GVN_OK;
+  if (!xv_current) {
+    const size_t n4 = (size_t)b->F * b->NP / 4;
+    k_pack_xv<<<148 * 8, 256, 0, st>>>(n4, reinterpret_cast<const float4*>(b->X2), reinterpret_cast<const float4*>(b->Vb),
+                                       reinterpret_cast<uint4*>(b->XV));
+    if ((rc = check_launch("k_pack_xv"))) return rc;
+  }
   static thread_local CUtensorMap mx;                   // encoded once per (pointer, shape)
   static thread_local const void* mx_ptr = nullptr;
   static thread_local int mx_F = 0, mx_NP = 0;

@@ -105,6 +105,17 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
 }
 // uniform in (0,1): 24 random bits + half an ulp
 __device__ __forceinline__ float u01(uint32_t x) { return ((x >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+// One word of XV (include/gvn.h): low half = bf16(Vb) (round to nearest); high half chosen so that the WHOLE word,
+// read as an f32, is the value nearest to X2 -- the low half then acts as extra mantissa bits of X2 (same 2^-9
+// relative bound as a bf16 rounding) and the chain epilogue needs no mask to take X2 out of the word.
+__device__ __forceinline__ uint32_t pack_xv_word(float x2, float vb) {
+  uint32_t vbits = __float_as_uint(fmaxf(vb, 0.f));
+  vbits += 0x7fffu + ((vbits >> 16) & 1u);                 // bf16 round to nearest even (finite, non-negative input)
+  const uint32_t lo = vbits >> 16;
+  const uint32_t xb = __float_as_uint(fmaxf(x2, 0.f));
+  const uint32_t hi = xb > lo ? (xb - lo + 0x8000u) >> 16 : 0u;
+  return (hi << 16) | lo;
+}
 // two standard normals from two 32-bit words (Box-Muller)
 __device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
   float r = sqrtf(-2.0f * __logf(u01(a)));

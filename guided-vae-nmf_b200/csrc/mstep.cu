@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(256) k_mstep_cols(int F, int K, int NP, int R,
                                                     const float* __restrict__ X2, const float* __restrict__ Vs,
                                                     const float* __restrict__ Vs_w, float* __restrict__ Vb, float* __restrict__ g, float* __restrict__ H,
                                                     const float* __restrict__ Wun, const float* __restrict__ cnorm,
-                                                    float* __restrict__ cost_part) {
+                                                    float* __restrict__ cost_part, uint32_t* __restrict__ XV) {
   __shared__ float red[MS_WARPS][KMAX][MS_TILE];
   __shared__ float red1[MS_WARPS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -176,8 +176,8 @@ __global__ void __launch_bounds__(256) k_mstep_cols(int F, int K, int NP, int R,
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) { if (k < K) vb = fmaf(__ldg(wb + (size_t)f * K + k), hn[k], vb); }
     const size_t o = (size_t)f * NP + gn;
-    if (valid) Vb[o] = vb;
     const float x2 = X2[o];
+    if (valid) { Vb[o] = vb; if (XV != nullptr) XV[o] = pack_xv_word(x2, vb); }
     float t2 = 0.f, t1 = 0.f;
 #pragma unroll 5
     for (int r = 0; r < R; ++r) {
@@ -344,10 +344,10 @@ int32_t launch_mstep(const gvn_batch* b, int R, float* cost_part, void* workspac
   if ((rc = check_launch("k_colnorm"))) return rc;
   if (b->K <= 16) {
     k_mstep_cols<16><<<ntiles, 256, 0, st>>>(b->F, b->K, b->NP, R, b->frame_utt, b->X2, b->Vs, b->Vs_w, b->Vb, b->g, b->H,
-                                             b->Wun, cnorm, cost_part);
+                                             b->Wun, cnorm, cost_part, b->XV);
   } else {
     k_mstep_cols<32><<<ntiles, 256, 0, st>>>(b->F, b->K, b->NP, R, b->frame_utt, b->X2, b->Vs, b->Vs_w, b->Vb, b->g, b->H,
-                                             b->Wun, cnorm, cost_part);
+                                             b->Wun, cnorm, cost_part, b->XV);
   }
   return check_launch("k_mstep_cols");
 }

@@ -262,7 +262,7 @@ struct ColsArgs {
   int F, K, KS, NP, R, B, ntiles, nchunk;
   const int32_t* frame_utt; const int32_t* frame_off;
   const float* X2t; const float* Vs; const float* Mt;
-  float* Vb; float* g; float* H; const float* Wun; float* W; float* cost_part;
+  float* Vb; float* g; float* H; const float* Wun; float* W; float* cost_part; uint32_t* XV;
 };
 
 constexpr int CCT = 384;              // compute threads of the column sweep: 12 warps (+1 producer) = at most 4 per scheduler
@@ -486,8 +486,10 @@ __global__ void __launch_bounds__(CTT, 1) k_cols_v1(ColsArgs p) {
     {
       const float* vs = data + (size_t)fl * NB + n;
       const float* wrow = W_s + fl * KS;
+      const size_t vstep = (size_t)CFL * NP;
       float* vbo = p.Vb + (size_t)fl * NP + (size_t)t * NB + n;
-      for (int i = 0; i < NI; ++i, vs += CFL * NB, wrow += CFL * KS, vbo += (size_t)CFL * NP) {
+      uint32_t* xvo = p.XV != nullptr ? p.XV + (size_t)fl * NP + (size_t)t * NB + n : nullptr;
+      for (int i = 0; i < NI; ++i, vs += CFL * NB, wrow += CFL * KS, vbo += vstep) {
         if (i * CFL + fl < F) {
           f2 vbp = F2(0.f, 0.f);
 #pragma unroll
@@ -496,7 +498,7 @@ __global__ void __launch_bounds__(CTT, 1) k_cols_v1(ColsArgs p) {
             vbp = fma2(F2(t4.x, t4.y), F2(hn[k4], hn[k4 + 1]), fma2(F2(t4.z, t4.w), F2(hn[k4 + 2], hn[k4 + 3]), vbp));
           }
           const float vb = vbp.x + vbp.y;
-          if (valid) *vbo = vb;
+          if (valid) { *vbo = vb; if (xvo != nullptr) xvo[(size_t)i * vstep] = pack_xv_word(vs[R * PS], vb); }
           float t1 = 0.f, t2 = 0.f;
           f2 t1v = F2(0.f, 0.f), t2v = F2(0.f, 0.f);
           const f2 g2 = F2(gg, gg), vb2 = F2(vb, vb);
@@ -632,7 +634,7 @@ struct GenArgs {
   int F, K, KS, NP, R, ntiles;
   const int32_t* frame_utt; const int32_t* frame_off;
   const float* X2t; const float* Vs; const float* Mt;
-  float* Vb; float* g; float* H; const float* Wun; float* W; float* cost_part;
+  float* Vb; float* g; float* H; const float* Wun; float* W; float* cost_part; uint32_t* XV;
 };
 constexpr int GT = 256;
 __host__ __device__ inline size_t gen_smem_floats(int F, int KS, int K, int R) {
@@ -733,7 +735,10 @@ __global__ void __launch_bounds__(GT, 2) k_cols_gen(GenArgs p) {
     float ng = 0.f, dg = 0.f;
     for (int f = fl; f < F; f += 32) {
       const float vb = dot_w(W_s + f * KS, hn);
-      if (valid) p.Vb[(size_t)f * NP + (size_t)t * NB + n] = vb;
+      if (valid) {
+        p.Vb[(size_t)f * NP + (size_t)t * NB + n] = vb;
+        if (p.XV != nullptr) p.XV[(size_t)f * NP + (size_t)t * NB + n] = pack_xv_word(__ldg(x2p + (size_t)f * NB), vb);
+      }
       a_s[f * NB + n] = vb;                                 // kept for the cost pass
       const float* vs = vs0 + (size_t)f * NB;
       float t1 = 0.f, t2 = 0.f;
@@ -900,7 +905,7 @@ int32_t launch_mstep_v1(const gvn_batch* b, int R, float* cost_part, float* Mt, 
     const int NI = (b->F + CFL - 1) / CFL;
     a.nchunk = NI < MAXCH ? NI : MAXCH;
     a.frame_utt = b->frame_utt; a.frame_off = b->frame_off; a.X2t = b->X2t; a.Vs = b->Vs; a.Mt = Mt;
-    a.Vb = b->Vb; a.g = b->g; a.H = b->H; a.Wun = b->Wun; a.W = b->W; a.cost_part = cost_part;
+    a.Vb = b->Vb; a.g = b->g; a.H = b->H; a.Wun = b->Wun; a.W = b->W; a.cost_part = cost_part; a.XV = b->XV;
     const size_t smem = cols_smem_floats(b->F, a.KS, b->K, R, KMAX) * 4;
     const int grid = a.ntiles < sms ? a.ntiles : sms;
     switch (KMAX) {
@@ -916,7 +921,7 @@ int32_t launch_mstep_v1(const gvn_batch* b, int R, float* cost_part, float* Mt, 
   GenArgs a;
   a.F = b->F; a.K = b->K; a.KS = ks_gen(b->K); a.NP = b->NP; a.R = R; a.ntiles = ntiles;
   a.frame_utt = b->frame_utt; a.frame_off = b->frame_off; a.X2t = b->X2t; a.Vs = b->Vs; a.Mt = Mt;
-  a.Vb = b->Vb; a.g = b->g; a.H = b->H; a.Wun = b->Wun; a.W = b->W; a.cost_part = cost_part;
+  a.Vb = b->Vb; a.g = b->g; a.H = b->H; a.Wun = b->Wun; a.W = b->W; a.cost_part = cost_part; a.XV = b->XV;
   const size_t smem = gen_smem_floats(b->F, a.KS, b->K, R) * 4;
   const int per_sm = smem <= 110 * 1024 ? 2 : 1;
   const int grid = ntiles < sms * per_sm ? ntiles : sms * per_sm;

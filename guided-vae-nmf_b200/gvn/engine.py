@@ -378,8 +378,10 @@ class ReplayNoise:
 
 
 def estep(batch, dec, burnin, R, var_RW, precision="fp32", seed=0, chain=0, eps=None, u=None, forced=None,
-          trace=False):
-    """One MH chain over all frames (gvn_estep).  Returns the trace tensors if requested."""
+          trace=False, xv_current=False):
+    """One MH chain over all frames (gvn_estep).  Returns the trace tensors if requested.
+    ``xv_current``: the caller vouches that gvn_mstep was the last writer of Vb (it keeps batch.XV, the packed
+    per-bin constants of the tensor-core chain, in step), so the packing pass is skipped."""
     lib = _lib.load()
     nz = GvnNoise()
     nz.eps, nz.u = (0 if eps is None else eps.data_ptr()), (0 if u is None else u.data_ptr())
@@ -397,7 +399,8 @@ def estep(batch, dec, burnin, R, var_RW, precision="fp32", seed=0, chain=0, eps=
         tr.z_samples = zs.data_ptr()
         out = (acc, dec_, cnt, zs)
     check(lib.gvn_estep(batch.struct(), _ptr(dec.packed), int(burnin), int(R), float(np.float32(var_RW)),
-                        C.byref(nz), C.byref(tr) if tr is not None else None, PRECISIONS[precision], _stream()))
+                        C.byref(nz), C.byref(tr) if tr is not None else None,
+                        PRECISIONS[precision] | (_lib.GVN_PREC_XV_CURRENT if xv_current else 0), _stream()))
     return out
 
 
@@ -483,12 +486,13 @@ def run_mcem(batch, dec, niter, chain_E, chain_WF, var_RW, precision="fp32", see
 
     for n in range(niter):
         e, u = (noise.chains[n] if noise is not None else (None, None))
-        timed("estep", estep, batch, dec, b_E, R_E, var_RW, precision, seed, n, e, u)
+        # after the first M-step XV is kept current by gvn_mstep (unless a hook may have touched Vb)
+        timed("estep", estep, batch, dec, b_E, R_E, var_RW, precision, seed, n, e, u, None, False, n > 0 and iter_hook is None)
         timed("mstep", mstep, batch, R_E, scratch, n, mstep_variant)
         if iter_hook is not None:
             iter_hook(batch, n)
     e, u = (noise.chains[niter] if noise is not None else (None, None))
-    timed("estep", estep, batch, dec, b_W, R_W, var_RW, precision, seed, niter, e, u)
+    timed("estep", estep, batch, dec, b_W, R_W, var_RW, precision, seed, niter, e, u, None, False, niter > 0 and iter_hook is None)
     cost = cost_reduce(batch, R_E, scratch, niter)
     S, Nn, WFs, WFn = wiener(batch, R_W, want_masks)
     return cost, S, Nn, WFs, WFn

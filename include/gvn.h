@@ -42,7 +42,9 @@
  *                        the previous sample (mcem.py:280-289), so sum_r phi(Vs_r) of the reference
  *                        equals sum_slot Vs_w[slot] * phi(Vs[slot]); nothing is ever copied.
  *                        sum_slot Vs_w[slot][n] == R for every frame.
- *    XV   [F][NP]    u32 scratch of the tensor-core chain: bf16(X2) << 16 | bf16(Vb)
+ *    XV   [F][NP]    u32 per-bin constants of the tensor-core chain, one word per (f, n): low half =
+ *                        bf16(Vb), high half such that the whole word read as f32 is nearest to X2.
+ *                        Written by gvn_estep (unless GVN_PREC_XV_CURRENT) and kept current by gvn_mstep.
  *    X2t  [NP/8][F][8] f32 X2 in column-tile order (built by gvn_init_nmf; read by gvn_mstep)
  *    yproj[HID][NP] f32  b1 + W1[:, L:] @ y  -- the label part of the decoder's first layer,
  *                        constant per utterance (mcem.py:242 concatenates y every step)
@@ -77,7 +79,11 @@ enum {
 enum {
   GVN_PREC_FP32 = 0,   /* CUDA-core fp32 FMA (bit-faithful mode, parity rtol 1e-4)           */
   GVN_PREC_F16X3 = 1,  /* tcgen05 f16 hi/lo split, 3 MMAs, fp32 accumulate in TMEM (~fp32)   */
-  GVN_PREC_F16 = 2     /* tcgen05 f16 operands, fp32 accumulate (11-bit mantissa, = TF32)    */
+  GVN_PREC_F16 = 2,    /* tcgen05 f16 operands, fp32 accumulate (11-bit mantissa, = TF32)    */
+  /* flag, OR-ed into `precision`: batch->XV already matches (X2, Vb).  gvn_mstep rewrites XV next to
+   * every Vb it writes, so inside the EM loop only the first gvn_estep has to pack it (the packing
+   * pass reads X2 and Vb and writes XV: 100 MB per launch at 64 utterances). */
+  GVN_PREC_XV_CURRENT = 0x100
 };
 
 typedef struct gvn_batch {

@@ -136,3 +136,31 @@ def test_tc_chain_other_latent_dims(L, y_dim):
     np.testing.assert_allclose(t["zs"], a["zs"], rtol=1e-6, atol=1e-6)
     np.testing.assert_allclose(t["Vs"], a["Vs"], rtol=5e-3)
     np.testing.assert_allclose(t["acc"], a["acc"], atol=0.25, rtol=2e-2)
+
+
+@pytest.mark.parametrize("K,variant", [(10, 1), (20, 1), (10, 0)])
+def test_xv_kept_current_by_mstep(K, variant):
+    """gvn_mstep rewrites XV next to every Vb it writes (staged sweep, generic sweep, variant 0), so a chain
+    launched with GVN_PREC_XV_CURRENT sees the words the packing pass would have produced: bit-identical runs."""
+    from gvn import engine as E
+    from gvn.pipeline import McemConfig, Enhancer
+    import bench
+    vae = bench.build_model()
+    cfg = McemConfig(model="M2", niter=3, nmf_rank=K, precision="f16", mstep_variant=variant)
+    enh = Enhancer(vae, cfg, "cuda:0")
+    x, s, nz, labels = bench.make_inputs(3, 0, T=12000)
+    res = []
+    for hook in (None, lambda b, n: None):                  # a hook disables the shortcut: every chain packs XV itself
+        b = enh.prepare(list(x), labels, seed=4)
+        cost, S, Nn, _, _ = E.run_mcem(b, enh.dec, 3, (10, 30), (25, 75), 0.01, "f16", 7, None, variant, iter_hook=hook)
+        torch.cuda.synchronize()
+        res.append((cost.cpu().numpy(), S.cpu().numpy(), b.XV.cpu().numpy().copy(), b.Vb.cpu().numpy().copy()))
+    np.testing.assert_array_equal(res[0][0], res[1][0])
+    np.testing.assert_array_equal(res[0][1], res[1][1])
+    # and the words themselves: low half = bf16(Vb), whole word as f32 within 2^-8 of X2
+    xv, vb = res[0][2].view(np.uint32), res[0][3]
+    valid = (b.frame_utt >= 0).cpu().numpy()
+    lo = (xv & 0xffff).astype(np.uint32) << 16
+    np.testing.assert_allclose(lo.view(np.float32)[:, valid], vb[:, valid], rtol=2.0 ** -8)
+    x2 = b.X2.cpu().numpy()
+    np.testing.assert_allclose(xv.view(np.float32)[:, valid], x2[:, valid], rtol=2.0 ** -8, atol=1e-30)
