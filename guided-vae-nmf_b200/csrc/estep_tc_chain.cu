@@ -37,30 +37,19 @@
 
 #include <type_traits>
 
-#include "gvn_common.cuh"
-#include "tc_common.cuh"
+#include "tc_chain_common.cuh"
 
 namespace gvn {
 
-using namespace tc;
-
 namespace {
 
-constexpr int TM = 128;                 // frames per tile (MMA M)
-constexpr int HID = GVN_HIDDEN;
 constexpr int NE = 256;                 // epilogue threads
 constexpr int NEW = NE / 32;            // epilogue warps
 constexpr int NTHREADS = 320;
-constexpr int SROWS = 32;               // frequency rows per TMA box
 constexpr int STAGE_BYTES = SROWS * TM * 4;
-constexpr int MAX_STAGES = 8;
 #ifndef GVN_TC_DEFAULT_VARIANT
 #define GVN_TC_DEFAULT_VARIANT 3
 #endif
-constexpr float W_SCALE_INV = 1.0f / 256.0f;
-constexpr float LOG2E = 1.4426950408889634f;
-constexpr float LN2 = 0.6931471805599453f;
-constexpr float SC3 = W_SCALE_INV * LOG2E;
 
 // TMEM column map (512 columns allocated)
 // The hidden-layer accumulator aliases output buffer 0 (the two are never live together), which
@@ -68,59 +57,7 @@ constexpr float SC3 = W_SCALE_INV * LOG2E;
 constexpr uint32_t COL_ACC0 = 0, COL_ACC1 = 128, COL_ACCH = 0, COL_YP = 256, COL_A = 384, COL_Z = 448;
 constexpr uint32_t COL_LOGU = 464, COL_EPS = 480;     // L16 == 16 only: noise of the next step, double-buffered (see PRE)
 
-struct TcArgs {
-  int F, FN, L, NP, burnin, R, nstage;
-  float sd;
-  const int32_t* frame_utt;
-  const float* g; const float* yproj;
-  float* Z; float* Vs; float* Vs_w;
-  const unsigned char* img;            // tensor-core operand image
-  size_t off_w1d, off_w2, off_w3, off_b3s;
-  const float* b2;
-  const float* eps; const float* u; const uint8_t* forced; uint64_t seed, chain;
-  float* t_acc; uint8_t* t_dec; int32_t* t_cnt; float* t_zs;
-  unsigned long long* prof;            // optional [grid][10 warps][16] cycle counters (gvn_debug_profile_buffer)
-};
-
-__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float tanh_approx(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-// two hidden units per MUFU instruction: the result is needed as an f16 pair (the next layer's A operand) anyway
-__device__ __forceinline__ uint32_t tanh_f16x2(float lo, float hi) {
-  uint32_t x = pack_f16(lo, hi), y;
-  asm("tanh.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x));
-  return y;
-}
-
-__device__ __forceinline__ void st_stream(float* p, float v) { asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
-
 __device__ __forceinline__ void bar_epilogue() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
-
-// XV[f][n] = pack_xv_word(X2, Vb) (gvn_common.cuh) for the whole batch: the chain's per-bin constants
-__global__ void __launch_bounds__(256) k_pack_xv(size_t n4, const float4* __restrict__ X2, const float4* __restrict__ Vb,
-                                                 uint4* __restrict__ XV) {
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
-    const float4 x = X2[i], v = Vb[i];
-    uint4 o;
-    o.x = pack_xv_word(x.x, v.x); o.y = pack_xv_word(x.y, v.y); o.z = pack_xv_word(x.z, v.z); o.w = pack_xv_word(x.w, v.w);
-    XV[i] = o;
-  }
-}
-
-// parity wait for the two single-lane service warps: suspends in hardware between polls so that
-// their spinning does not take issue slots from the epilogue warps of the same scheduler
-__device__ __forceinline__ void mbar_wait_idle(uint64_t* bar, uint32_t parity) {
-  uint32_t ok = 0;
-  for (uint32_t spins = 0; !ok; ++spins) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(20000u) : "memory");
-    if (spins > (1u << 16)) __trap();         // ~1 s: a protocol bug must fail fast
-  }
-}
 
 template <int L16, bool PROF_ON, int VAR>
 __global__ void __launch_bounds__(NTHREADS, 1) k_estep_tc(const __grid_constant__ CUtensorMap tm_xv, TcArgs p) {
@@ -611,37 +548,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_estep_tc(const __grid_constant_
 }
 
 // ---- host side -------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn encode_tiled_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (fn == nullptr) {
-    void* sym = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(sym);
-  }
-  return fn;
-}
-
-// [F][NP] u32 array, box = [SROWS rows][128 frames]
-int32_t make_tile_map(CUtensorMap* m, const uint32_t* base, int F, int NP) {
-  EncodeTiledFn fn = encode_tiled_fn();
-  if (fn == nullptr) return fail(GVN_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
-  cuuint64_t gdim[2] = {(cuuint64_t)NP, (cuuint64_t)F};
-  cuuint64_t gstride[1] = {(cuuint64_t)NP * 4};
-  cuuint32_t box[2] = {(cuuint32_t)TM, (cuuint32_t)SROWS};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<uint32_t*>(base), gdim, gstride, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return fail(GVN_E_CUDA, "cuTensorMapEncodeTiled failed with %d", (int)r);
-  return GVN_OK;
-}
-
 template <int L16, bool PROF_ON, int VAR>
 int32_t launch_tc(const CUtensorMap& mx, const TcArgs& a, int grid, cudaStream_t st) {
   const size_t fixed = (size_t)HID * 2 * L16 * 2 + (size_t)HID * HID * 2 + (size_t)a.FN * HID * 2 + (size_t)(a.FN + 16 + HID) * 4 +
@@ -691,7 +597,7 @@ int32_t launch_estep_tc(const gvn_batch* b, const void* packed, int burnin, int 
   static thread_local const void* mx_ptr = nullptr;
   static thread_local int mx_F = 0, mx_NP = 0;
   if (mx_ptr != b->XV || mx_F != b->F || mx_NP != b->NP) {
-    if ((rc = make_tile_map(&mx, b->XV, b->F, b->NP))) return rc;
+    if ((rc = make_tile_map(&mx, b->XV, b->F, b->NP, TM))) return rc;
     mx_ptr = b->XV; mx_F = b->F; mx_NP = b->NP;
   }
   TcArgs a;
