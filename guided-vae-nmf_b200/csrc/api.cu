@@ -33,6 +33,7 @@ int32_t launch_estep_simt(const gvn_batch*, const void*, int, int, float, const 
 int32_t launch_estep_tc(const gvn_batch*, const void*, int, int, float, const gvn_noise*, const gvn_trace*, int, cudaStream_t);
 size_t mstep_workspace_bytes(const gvn_batch*);
 int32_t launch_mstep(const gvn_batch*, int, float*, void*, int, cudaStream_t);
+int32_t launch_mstep_gain(const gvn_batch*, int, float*, cudaStream_t);
 int32_t launch_cost_reduce(const gvn_batch*, int, int, const float*, double*, cudaStream_t);
 int32_t launch_wiener(const gvn_batch*, int, float*, float*, float*, float*, cudaStream_t);
 int32_t launch_init_nmf(const gvn_batch*, const float*, const float*, float, cudaStream_t);
@@ -118,6 +119,14 @@ int32_t gvn_mstep(const gvn_batch* batch, int32_t R, float* cost_part, void* wor
   GVN_REQUIRE(cost_part && workspace, GVN_E_INVALID, "NULL pointer");
   GVN_REQUIRE(R >= 1 && R <= batch->R_cap, GVN_E_INVALID, "R=%d R_cap=%d", R, batch->R_cap);
   return launch_mstep(batch, R, cost_part, workspace, variant, (cudaStream_t)stream);
+}
+
+int32_t gvn_mstep_gain(const gvn_batch* batch, int32_t R, float* cost_part, void* stream) {
+  int32_t rc = check_batch(batch, false);
+  if (rc) return rc;
+  GVN_REQUIRE(cost_part && batch->X2t && batch->Vs && batch->Vs_w && batch->Vb && batch->g, GVN_E_INVALID, "NULL pointer");
+  GVN_REQUIRE(R >= 1 && R <= batch->R_cap, GVN_E_INVALID, "R=%d R_cap=%d", R, batch->R_cap);
+  return launch_mstep_gain(batch, R, cost_part, (cudaStream_t)stream);
 }
 
 int32_t gvn_cost_reduce(const gvn_batch* batch, int32_t R, int32_t niter, const float* cost_part, double* cost,

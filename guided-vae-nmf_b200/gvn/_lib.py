@@ -45,6 +45,7 @@ SIGNATURES = {
     "gvn_estep": (_i, [C.POINTER(GvnBatch), _p, _i, _i, C.c_float, C.POINTER(GvnNoise), C.POINTER(GvnTrace), _i, _p]),
     "gvn_mstep_workspace_bytes": (C.c_size_t, [C.POINTER(GvnBatch)]),
     "gvn_mstep": (_i, [C.POINTER(GvnBatch), _i, _p, _p, _i, _p]),
+    "gvn_mstep_gain": (_i, [C.POINTER(GvnBatch), _i, _p, _p]),
     "gvn_cost_reduce": (_i, [C.POINTER(GvnBatch), _i, _i, _p, _p, _p]),
     "gvn_wiener": (_i, [C.POINTER(GvnBatch), _i, _p, _p, _p, _p, _p]),
     "gvn_stft_power": (_i, [C.POINTER(GvnBatch), _p, _i, _p, _p, _i, _i, _p]),

@@ -417,6 +417,12 @@ def mstep(batch, R, scratch, it, variant=1):
     check(lib.gvn_mstep(batch.struct(), int(R), _ptr(scratch.cost_part[it]), _ptr(scratch.ws), int(variant), _stream()))
 
 
+def mstep_gain(batch, R, scratch, it):
+    """Gain-only M-step with a fixed noise variance (EM_noNMF.M_step, mcem.py:551-588) + cost."""
+    lib = _lib.load()
+    check(lib.gvn_mstep_gain(batch.struct(), int(R), _ptr(scratch.cost_part[it]), _stream()))
+
+
 def cost_reduce(batch, R, scratch, niter):
     lib = _lib.load()
     cost = torch.empty(niter, batch.B, dtype=torch.float64, device=batch.device)

@@ -1,6 +1,8 @@
 """Drop-in for the reference's ``python/models/mcem.py`` -- same class names, constructor and
 method signatures and public attributes -- backed by the sm_100a kernels of libgvn.so.
 
+``EM_noNMF`` / ``MCEM_M2_noNMF`` (mcem.py:493-760, fixed noise variance, gain-only M-step) follow at the end.
+
 ``MCEM_M1`` / ``MCEM_M2`` keep the single-utterance API of the reference
 (``init_parameters`` -> ``run`` -> ``S_hat`` / ``N_hat``; mcem.py:185-216, :350-369, :155-178);
 underneath it is a batch of one on the engine in ``gvn.engine``.  The batched entry point
@@ -231,3 +233,89 @@ class MCEM_M1(EM):
         """Same signature as mcem.py:371 (``y`` is unused there too).  Returns Z_sampled (N,R,L)."""
         self._run_chain(nsamples, burnin, Z=Z, trace=True)
         return self.last_trace["z_samples"].permute(2, 0, 1).contiguous()
+
+
+class EM_noNMF(EM):
+    """Reference mcem.py:493-607: the noise variance ``Vb`` is given and fixed, the M-step updates the gain
+    only (``gvn_mstep_gain``).  Same constructor as the reference (everything arrives in ``__init__``; X and Vb
+    are (N,F))."""
+
+    def __init__(self, X, Vb, g, vae, niter=100, device="cpu"):
+        EM.__init__(self, niter=niter)
+        self._ctor = dict(X=X, Vb=Vb, g=g, vae=vae, device=device)
+
+    def _init_fixed_noise(self, Z, y):
+        c = self._ctor
+        vae, device = c["vae"], c["device"]
+        if type(vae).__name__ == "RVAE":
+            raise NameError("MCEM algorithm only valid for FFNN VAE")
+        dev = _E._require_cuda(device)
+        self.device = device
+        X = np.asarray(c["X"])
+        N, F = X.shape
+        dec = _E.PackedDecoder(vae, dev)
+        (R_E, _), (R_W, _) = self.chain_lengths()
+        f32 = dict(dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            b = _E.Batch([N], F, 1, dec.L, max(R_E, R_W), dev)          # K = 1: W / H are allocated but never used
+            self._batch, self._dec, self.vae = b, dec, vae
+            self.X = X.T
+            Xt = np.ascontiguousarray(X.T.astype(np.complex64))
+            b.Xc[:, b.cols(0), :] = torch.from_numpy(Xt.view(np.float32).reshape(F, N, 2)).to(dev)
+            b.scatter_cols(b.X2, [torch.from_numpy((np.abs(X.T) ** 2).astype(np.float32))])       # mcem.py:505
+            b.X2t.copy_(b.X2.reshape(F, b.NP // 8, 8).permute(1, 0, 2))
+            b.scatter_cols(b.Vb, [torch.as_tensor(np.asarray(c["Vb"]).T).to(**f32)])              # :508
+            b.scatter_cols(b.g, [torch.as_tensor(c["g"]).to(**f32).reshape(-1)])                  # :509
+            b.scatter_cols(b.Z, [torch.t(torch.as_tensor(Z).to(**f32))])                          # :623
+            yd = torch.zeros(dec.y_dim, b.NP, **f32)
+            b.scatter_cols(yd, [torch.t(torch.as_tensor(y).to(**f32))])                           # :624
+            self.y = yd[:, b.cols(0)]
+            _E.set_labels(b, dec, yd)
+        self.X_abs_2_t = self.X_abs_2
+        self._R = None
+        self._iter = 0
+        self._scratch = None
+        self._chain = 0
+        self._replay_pos = 0
+        if self.seed is None:
+            _chain_counter[0] += 1
+            self._seed = (torch.initial_seed() * 0x9E3779B97F4A7C15 + _chain_counter[0]) & (2 ** 63 - 1)
+        else:
+            self._seed = int(self.seed)
+
+    W = property(lambda self: None)
+    H = property(lambda self: None)
+
+    # ---- mcem.py:551-588 (+ the cost of :530-532) ----
+    def M_step(self):
+        b = self._batch
+        if self._scratch is None:
+            self._scratch = _E.MstepScratch(b, max(1, self.niter))
+        with torch.cuda.device(b.device):
+            _E.mstep_gain(b, self._R, self._scratch, self._iter % max(1, self.niter))
+        self._last_iter = self._iter % max(1, self.niter)
+        self._iter += 1
+
+
+class MCEM_M2_noNMF(EM_noNMF):
+    """Reference mcem.py:609-760.  Like the reference's constructor (mcem.py:505-509, :623-624) this one places the
+    state on the device right away.  ``replay`` (dict(eps, u[, forced])) and ``precision`` may be set on the object
+    before the first chain, as for the other classes."""
+
+    def __init__(self, X, Vb, g, Z, y, vae, niter, device, nsamples_E_step=10, burnin_E_step=30, nsamples_WF=25,
+                 burnin_WF=75, var_RW=0.01):
+        super().__init__(X=X, Vb=Vb, g=g, vae=vae, niter=niter, device=device)
+        if type(vae).__name__ == "RVAE":
+            raise NameError("MCEM algorithm only valid for FFNN VAE")
+        self.nsamples_E_step = nsamples_E_step
+        self.burnin_E_step = burnin_E_step
+        self.nsamples_WF = nsamples_WF
+        self.burnin_WF = burnin_WF
+        self.var_RW = var_RW
+        self._init_fixed_noise(Z, y)
+
+    def sample_posterior(self, Z, y, nsamples=10, burnin=30):
+        self._run_chain(nsamples, burnin, Z=Z, trace=True)
+        zs = self.last_trace["z_samples"].permute(2, 0, 1).contiguous()
+        yy = torch.t(self.y).unsqueeze(1).expand(zs.shape[0], zs.shape[1], self.y.shape[0])
+        return zs, torch.cat([zs, yy], dim=2)

@@ -65,6 +65,7 @@ extern "C" {
 #define GVN_HIDDEN 128          /* decoder hidden width (h_dim=[128,128] in every script) */
 #define GVN_MAX_K 32            /* NMF rank limit */
 #define GVN_MAX_L 64            /* latent dimension limit */
+#define GVN_MAX_R_SLOTS 128     /* sample-slot limit of gvn_mstep_gain */
 
 enum {
   GVN_OK = 0,
@@ -162,6 +163,12 @@ int32_t gvn_mstep(const gvn_batch* batch /*HOST*/, int32_t R, float* cost_part, 
 int32_t gvn_cost_reduce(const gvn_batch* batch /*HOST*/, int32_t R, int32_t niter,
                         const float* cost_part /*[niter][NP/8]*/, double* cost /*[niter][B]*/,
                         void* stream);
+
+/* Gain-only M-step of the models without an NMF noise dictionary: replaces EM_noNMF.M_step +
+ * compute_expected_neg_log_like (mcem.py:551-588, :530-532; used by MCEM_M2_noNMF :609-760).  batch->Vb is an
+ * input that stays fixed; updates g in place and writes the cost partials like gvn_mstep (same gvn_cost_reduce).
+ * Reads X2t, Vs, Vs_w, Vb, g; W / H are not touched. */
+int32_t gvn_mstep_gain(const gvn_batch* batch /*HOST*/, int32_t R, float* cost_part, void* stream);
 
 /* Wiener filter from the R kept samples of the final chain: replaces the tail of
  * compute_WF and EM.run (mcem.py:341-343, :175-176).  S_hat/N_hat are [F][NP] c64;

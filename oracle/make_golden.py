@@ -18,6 +18,8 @@ Run from the repo root (the reference tree is read-only, so no bytecode is writt
   ``mcem.py:155-178``), the state after every step is stored, and a second instance is run
   through ``run()`` itself to check that the stepwise drive is the same computation.
 
+* ``mcem_M2_noNMF.npz`` -- the same drive for ``MCEM_M2_noNMF`` (``mcem.py:609-760``).
+
 /root/reference does not exist on the GPU box; only the committed .npz files travel.
 """
 import os
@@ -191,9 +193,65 @@ def golden_mcem(tag, model, y_kind, L, K, niter, chain, T=6144, seed=0):
     print("golden %-7s N=%d L=%d K=%d niter=%d steps=%d cost=%s" % (tag, N, L, K, niter, len(u_), np.round(cost, 4)))
 
 
+def golden_nonmf(tag="M2_noNMF", L=16, niter=3, chain=(3, 4, 3, 5), T=6144, seed=0):
+    """MCEM_M2_noNMF (mcem.py:609-760): fixed noise variance, gain-only M-step.  Same drive as golden_mcem."""
+    ref_mcem, ref_models = _reference_modules()
+    nE, bE, nW, bW = chain
+    x, s, _ = synth_utterance(0, seed=seed, T=T)
+    X = stft_oracle.stft(x, **STFT_KW).T
+    N, F = X.shape
+    torch.manual_seed(0)
+    vae = ref_models.DeepGenerativeModel([F, 1, L, [128, 128]], None)
+    vae.eval()
+    for p in vae.parameters():
+        p.requires_grad = False
+    with torch.no_grad():
+        vae.decoder.reconstruction.bias.copy_(torch.linspace(-6.0, -1.0, F))
+        vae.decoder.hidden[0].bias.normal_(0, 0.3)
+        vae.decoder.hidden[1].bias.normal_(0, 0.3)
+    rs = np.random.RandomState(11)
+    P = np.abs(X) ** 2
+    Vb = (0.5 * P.mean(0, keepdims=True) * (0.5 + rs.rand(N, F))).astype(np.float32)       # (N,F) as the constructor takes it
+    g0 = torch.from_numpy((0.5 + rs.rand(N)).astype(np.float32))
+    Z0 = torch.from_numpy((0.3 * rs.randn(N, L)).astype(np.float32))
+    y = (torch.from_numpy(rs.rand(N, 1).astype(np.float32)) > 0.4).float()
+
+    def make(tape):
+        ref_mcem.torch = _TorchProxy(tape)
+        return ref_mcem.MCEM_M2_noNMF(X=X, Vb=Vb, g=g0.clone(), Z=Z0.clone(), y=y, vae=vae, niter=niter, device="cpu",
+                                      nsamples_E_step=nE, burnin_E_step=bE, nsamples_WF=nW, burnin_WF=bW, var_RW=0.01)
+
+    tape = NoiseTape(seed=4321 + seed)
+    m = make(tape)
+    flat, cost, Vs_first = {}, [], None
+    for n in range(niter):
+        m.E_step()
+        flat["E%d_Z" % n] = m.Z.numpy().copy()
+        if n == 0:
+            Vs_first = m.Vs.numpy().copy()
+        m.M_step()
+        cost.append(float(m.compute_expected_neg_log_like()))
+        flat["M%d_g" % n] = m.g.numpy().copy()
+    WFs, WFn = m.compute_WF(sample=True)
+    S_hat, N_hat = WFs.numpy() * m.X, WFn.numpy() * m.X
+    m2 = make(NoiseTape(draws=tape.draws))
+    cost2 = m2.run()
+    assert np.array_equal(cost2, np.array(cost)), (cost2, cost)
+    assert np.array_equal(m2.S_hat, S_hat) and np.array_equal(m2.N_hat, N_hat)
+    ref_mcem.torch = torch
+    eps_ = np.stack([t.numpy() for k, t in tape.draws if k == "randn"])
+    u_ = np.stack([t.numpy() for k, t in tape.draws if k == "rand"])
+    sd = {"sd_" + k: v.numpy() for k, v in vae.state_dict().items()}
+    np.savez_compressed(os.path.join(OUT, "mcem_%s.npz" % tag), L=L, niter=niter, chain=np.array(chain), var_RW=0.01,
+                        X=X, Vb=Vb, g0=g0.numpy(), Z0=Z0.numpy(), y=y.numpy(), tape_eps=eps_, tape_u=u_, cost=np.array(cost),
+                        S_hat=S_hat, N_hat=N_hat, WFs=WFs.numpy(), WFn=WFn.numpy(), Vs_E0=Vs_first, **flat, **sd)
+    print("golden %-8s N=%d L=%d niter=%d steps=%d cost=%s" % (tag, N, L, niter, len(u_), np.round(cost, 4)))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     golden_stft()
     golden_mcem("M1", "M1", None, L=16, K=4, niter=2, chain=(3, 4, 2, 5))
     golden_mcem("M2_ibm", "M2", "ibm", L=16, K=10, niter=3, chain=(3, 5, 4, 6))
     golden_mcem("M2_vad", "M2", "vad", L=32, K=10, niter=2, chain=(2, 3, 2, 3))
+    golden_nonmf()

@@ -19,6 +19,8 @@ What it restates (reference files relative to /root/reference)
 * ``python/models/mcem.py:68-70``       cost                     -> :meth:`McemOracle.cost`
 * ``python/models/mcem.py:327-345 / 473-490`` compute_WF         -> :meth:`McemOracle.compute_WF`
 * ``python/models/mcem.py:155-178``     EM.run                   -> :meth:`McemOracle.run`
+* ``python/models/mcem.py:493-607``     EM_noNMF (fixed noise variance, gain-only M-step)
+  and ``:609-760`` MCEM_M2_noNMF                                  -> :class:`McemNoNmfOracle`
 
 It is written with the same torch CPU ops in the same order as the reference (so that in
 fp32 it reproduces the reference bit-for-bit when both consume the same noise tape), but
@@ -277,6 +279,33 @@ class McemOracle:
         self.S_hat = WFs.to(torch.float32).numpy() * self.X
         self.N_hat = WFn.to(torch.float32).numpy() * self.X
         return cost
+
+
+class McemNoNmfOracle(McemOracle):
+    """MCEM_M2_noNMF (mcem.py:609-760) on EM_noNMF (mcem.py:493-607): the noise variance Vb is given
+    and stays fixed, the M-step updates the gain only.  The chain, compute_Vs, the cost and the Wiener
+    filter are the M2 ones (the reference repeats their code verbatim)."""
+
+    def __init__(self, X, Vb, g, Z, y, dec, niter, tape, nsamples_E_step=10, burnin_E_step=30, nsamples_WF=25,
+                 burnin_WF=75, var_RW=0.01, dtype=torch.float32):
+        super().__init__(niter, nsamples_E_step, burnin_E_step, nsamples_WF, burnin_WF, var_RW, model="M2", dtype=dtype)
+        self.tape = tape
+        self.X = np.asarray(X).T                                              # mcem.py:504
+        self.X_abs_2 = torch.from_numpy((np.abs(np.asarray(X).T) ** 2).astype(np.float32)).to(dtype)   # :505
+        self.Vb = torch.tensor(np.asarray(Vb).T).to(dtype)                    # :508
+        self.g = torch.as_tensor(g).to(dtype)                                 # :509
+        self.Z = torch.t(torch.as_tensor(Z).to(dtype))                        # :623
+        self.y = torch.t(torch.as_tensor(y).to(dtype))                        # :624
+        self.dec = {k: v.to(dtype) for k, v in dec.items()}
+        self.Vs = self.Vs_scaled = self.Vx = None
+
+    # mcem.py:551-588
+    def M_step(self):
+        self.Vx = self.Vs_scaled + self.Vb
+        num = torch.sum(self.X_abs_2 * torch.sum(self.Vs * (self.Vx ** -2), axis=0), axis=0)
+        den = torch.sum(torch.sum(self.Vs * (self.Vx ** -1), axis=0), axis=0)
+        self.g = self.g * (num / den) ** .5
+        self._refresh()
 
 
 # ----------------------------------------------------------------------------------------

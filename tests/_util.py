@@ -4,7 +4,7 @@ import os
 import numpy as np
 import torch
 
-from oracle.mcem_oracle import McemOracle, NoiseTape, split_state_dict
+from oracle.mcem_oracle import McemNoNmfOracle, McemOracle, NoiseTape, split_state_dict
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
@@ -36,3 +36,20 @@ def oracle_from_golden(g, dtype=torch.float32):
     o.init_parameters(g["X"], y, split_state_dict(sd, "decoder"), split_state_dict(sd, "encoder"),
                       int(g["K"]), float(g["eps"]), NoiseTape(draws=golden_tape(g), dtype=dtype))
     return o
+
+
+def nonmf_tape(g):
+    draws = []
+    for e, u in zip(g["tape_eps"], g["tape_u"]):
+        draws.append(("randn", torch.from_numpy(e)))
+        draws.append(("rand", torch.from_numpy(u)))
+    return draws
+
+
+def nonmf_oracle_from_golden(g, dtype=torch.float32):
+    """MCEM_M2_noNMF restatement fed with the golden inputs (tests/golden/mcem_M2_noNMF.npz)."""
+    nE, bE, nW, bW = [int(v) for v in g["chain"]]
+    sd = golden_state_dict(g)
+    return McemNoNmfOracle(g["X"], g["Vb"], torch.from_numpy(g["g0"]), torch.from_numpy(g["Z0"]), torch.from_numpy(g["y"]),
+                           split_state_dict(sd, "decoder"), int(g["niter"]), NoiseTape(draws=nonmf_tape(g), dtype=dtype),
+                           nE, bE, nW, bW, float(g["var_RW"]), dtype=dtype)

@@ -7,7 +7,7 @@ import pytest
 import torch
 
 from oracle import stft_oracle
-from _util import GOLDEN, load_golden, oracle_from_golden
+from _util import GOLDEN, load_golden, nonmf_oracle_from_golden, oracle_from_golden
 
 STFT_KW = dict(fs=16000, wlen_sec=64e-3, win="hann", hop_percent=0.25, dtype="complex64")
 
@@ -79,3 +79,24 @@ def test_oracle_fp64_close_to_fp32():
     o = oracle_from_golden(g, dtype=torch.float64)
     cost = o.run()
     np.testing.assert_allclose(cost, g["cost"], rtol=2e-3)
+
+
+def test_nonmf_oracle_reproduces_reference_run():
+    # MCEM_M2_noNMF (mcem.py:609-760): fixed Vb, gain-only M-step
+    g = load_golden("M2_noNMF")
+    o = nonmf_oracle_from_golden(g)
+    seen = {}
+
+    def hook(oo, n):
+        seen[n] = dict(g=oo.g.numpy().copy(), Z=oo.Z.numpy().copy())
+        if n == 0:
+            seen["Vs0"] = oo.Vs.numpy().copy()
+    o.iter_hook = hook
+    cost = o.run()
+    np.testing.assert_array_equal(cost, g["cost"])
+    for n in range(int(g["niter"])):
+        np.testing.assert_array_equal(seen[n]["g"], g["M%d_g" % n])
+        np.testing.assert_array_equal(seen[n]["Z"], g["E%d_Z" % n])
+    np.testing.assert_array_equal(seen["Vs0"], g["Vs_E0"])
+    np.testing.assert_array_equal(o.S_hat, g["S_hat"])
+    np.testing.assert_array_equal(o.N_hat, g["N_hat"])
