@@ -35,6 +35,7 @@ size_t mstep_workspace_bytes(const gvn_batch*);
 int32_t launch_mstep(const gvn_batch*, int, float*, void*, int, cudaStream_t);
 int32_t launch_mstep_gain(const gvn_batch*, int, float*, cudaStream_t);
 int32_t launch_cost_reduce(const gvn_batch*, int, int, const float*, double*, cudaStream_t);
+int32_t launch_spp_mask(const gvn_batch*, float, float, float, float, int, float*, float*, cudaStream_t);
 int32_t launch_wiener(const gvn_batch*, int, float*, float*, float*, float*, cudaStream_t);
 int32_t launch_init_nmf(const gvn_batch*, const float*, const float*, float, cudaStream_t);
 int32_t launch_stft_power(const gvn_batch*, const float*, int, const int32_t*, const int32_t*, int, int, cudaStream_t);
@@ -190,6 +191,15 @@ uint64_t gvn_launch_count(void) { return g_launches; }
 int32_t gvn_selftest_umma(const float* A, const float* W, int32_t N, int32_t K, int32_t variant, float* D, void* stream) {
   GVN_REQUIRE(A && W && D, GVN_E_INVALID, "NULL pointer");
   return launch_selftest_umma(A, W, N, K, variant, D, (cudaStream_t)stream);
+}
+
+int32_t gvn_spp_mask(const gvn_batch* batch, float fixed_smooth, float prob_smooth, float prior, float snr_opt_db,
+                     int32_t n_init, float* soft, float* hard, void* stream) {
+  int32_t rc = check_batch(batch, false);
+  if (rc) return rc;
+  GVN_REQUIRE(batch->X2 && (soft || hard), GVN_E_INVALID, "NULL pointer");
+  GVN_REQUIRE(prior > 0.f && prior < 1.f && n_init >= 0, GVN_E_INVALID, "prior=%g n_init=%d", (double)prior, n_init);
+  return launch_spp_mask(batch, fixed_smooth, prob_smooth, prior, snr_opt_db, n_init, soft, hard, (cudaStream_t)stream);
 }
 
 int32_t gvn_init_nmf(const gvn_batch* batch, const float* rand_W, const float* rand_H, float eps, void* stream) {

@@ -52,6 +52,7 @@ SIGNATURES = {
     "gvn_istft_workspace_bytes": (C.c_size_t, [C.POINTER(GvnBatch), _i]),
     "gvn_istft": (_i, [C.POINTER(GvnBatch), _p, _i, _i, _p, _p, _i, _p, _p]),
     "gvn_dense": (_i, [_p, _p, _p, _i, _p, _i, _p, _p, C.c_float, _i, _i, _i, _p, _p]),
+    "gvn_spp_mask": (_i, [C.POINTER(GvnBatch), C.c_float, C.c_float, C.c_float, C.c_float, _i, _p, _p, _p]),
     "gvn_init_nmf": (_i, [C.POINTER(GvnBatch), _p, _p, C.c_float, _p]),
     "gvn_energy_ratios": (_i, [_p, _p, _p, _i, _i, _p, _p, _p]),
     "gvn_selftest_umma": (_i, [_p, _p, _i, _i, _i, _p, _p]),

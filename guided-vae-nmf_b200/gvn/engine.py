@@ -352,6 +352,18 @@ def classify(batch, classifier, mean=None, std=None, eps=0.0, hard=True):
     return dense(W, b, h, None, "hard" if hard else "sigmoid", batch.NP)
 
 
+def spp_mask(batch, fixed_smooth=0.8, prob_smooth=0.9, prior=0.5, snr_opt_db=15.0, n_init=10, want_soft=True):
+    """"timo" guide labels (python/models/spp_estimation.py:198-218): speech presence probability of every bin of
+    batch.X2 and its threshold at 0.5.  Returns (soft or None, hard), both [F][NP] on the device."""
+    lib = _lib.load()
+    f32 = dict(dtype=torch.float32, device=batch.device)
+    soft = torch.zeros(batch.F, batch.NP, **f32) if want_soft else None
+    hard = torch.zeros(batch.F, batch.NP, **f32)
+    check(lib.gvn_spp_mask(batch.struct(), float(fixed_smooth), float(prob_smooth), float(prior), float(snr_opt_db),
+                           int(n_init), _ptr(soft), _ptr(hard), _stream()))
+    return soft, hard
+
+
 # --------------------------------------------------------------------------------------
 # the MCEM loop (mcem.py:155-178)
 # --------------------------------------------------------------------------------------

@@ -23,7 +23,7 @@ from . import engine as E
 from . import wavio
 from .shard import shard_list
 
-LABEL_SOURCES = (None, "classifier", "oracle_ibm", "oracle_vad")
+LABEL_SOURCES = (None, "classifier", "timo", "oracle_ibm", "oracle_vad")
 
 
 def _stem(file_path):
@@ -53,7 +53,8 @@ def _write_item(output_dir, file_path, s_hat, n_hat, fs, y_soft, y_hard):
 def evaluate_file_list(enhancer, file_paths, processed_dir, output_dir, label_source=None, batch_size=64, seed=0,
                        quantile_fraction=0.999, quantile_weight=0.999, world=1, rank=0, io_threads=8, progress=None):
     """Enhances this rank's shard of ``file_paths``.  ``label_source``: None (M1), "classifier" (the enhancer's
-    supervised classifier), "oracle_ibm" / "oracle_vad" (from ``<stem>_s.wav``, target.py:7-50).
+    supervised classifier), "timo" (speech presence probability of the mixture itself, spp_estimation.py:198-218),
+    "oracle_ibm" / "oracle_vad" (from ``<stem>_s.wav``, target.py:7-50).
     Returns the list of (file_path, cost (niter,) float64) of the shard."""
     if label_source not in LABEL_SOURCES:
         raise ValueError("label_source must be one of %r" % (LABEL_SOURCES,))
@@ -62,6 +63,8 @@ def evaluate_file_list(enhancer, file_paths, processed_dir, output_dir, label_so
         raise ValueError("model %s and label_source %r do not go together" % (cfg.model, label_source))
     if label_source == "classifier" and enhancer.classifier is None:
         raise ValueError("label_source='classifier' needs an Enhancer built with a classifier")
+    if label_source == "timo":
+        enhancer.label_source = "timo"
     files = shard_list(list(file_paths), world, rank)
     groups = [files[i:i + batch_size] for i in range(0, len(files), batch_size)]
     oracle = label_source in ("oracle_ibm", "oracle_vad")
@@ -88,8 +91,10 @@ def evaluate_file_list(enhancer, file_paths, processed_dir, output_dir, label_so
                 y_soft = y_hard = None
                 if cfg.model == "M2":
                     y_hard = b.y
-                    y_soft = (E.classify(b, enhancer.classifier, enhancer.mean, enhancer.std, cfg.eps, hard=False)
-                              if label_source == "classifier" else b.y)
+                    if label_source == "classifier":
+                        y_soft = E.classify(b, enhancer.classifier, enhancer.mean, enhancer.std, cfg.eps, hard=False)
+                    else:
+                        y_soft = b.y_soft if label_source == "timo" else b.y
                 s_hat, n_hat, cost = enhancer.run(b, seed=seed + gi)
                 tag = str(gi & 1)                                                # two sets of pinned result buffers
                 s_h, n_h, c_h = E.download(s_hat, "ev_s" + tag), E.download(n_hat, "ev_n" + tag), E.download(cost, "ev_c" + tag)

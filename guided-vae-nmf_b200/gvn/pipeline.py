@@ -43,8 +43,11 @@ class McemConfig:
 class Enhancer:
     """Holds the packed model on one device and enhances batches of utterances."""
 
-    def __init__(self, vae, cfg, device, classifier=None, mean=None, std=None):
+    def __init__(self, vae, cfg, device, classifier=None, mean=None, std=None, label_source=None):
+        """``label_source`` for M2 when no labels are passed in: None = the classifier (evaluate_M2_ibm.py:121-131),
+        "timo" = the speech-presence-probability mask (:136-141; needs y_dim == F)."""
         self.device = E._require_cuda(device)
+        self.label_source = label_source
         self.cfg = cfg
         self.vae = vae
         self.classifier = classifier
@@ -115,7 +118,12 @@ class Enhancer:
                 E.init_nmf(b, cfg.eps, rand[0], rand[1])
             y = None
             if cfg.model == "M2":
-                y = up["y"] if up["y"] is not None else E.classify(b, self.classifier, self.mean, self.std, cfg.eps)
+                if up["y"] is not None:
+                    y = up["y"]
+                elif self.label_source == "timo":
+                    b.y_soft, y = E.spp_mask(b)
+                else:
+                    y = E.classify(b, self.classifier, self.mean, self.std, cfg.eps)
             E.set_labels(b, self.dec, y)
             E.encode_init(b, self.vae)
         b.T, b.T_stride, b.nfft, b.hop = up["T"], up["T_stride"], nfft, hop

@@ -199,6 +199,14 @@ int32_t gvn_dense(const float* W, const float* b, const float* in0, int32_t D0, 
                   int32_t D1, const float* mean, const float* std_, float eps, int32_t D_out,
                   int32_t NP, int32_t act, float* out, void* stream);
 
+/* "timo" guide labels: the speech presence probability of every time-frequency bin of batch->X2 from the
+ * SPP-based noise tracker.  Replaces timo_mask_estimation / SPPNoiseEstimator.update
+ * (python/models/spp_estimation.py:198-218, :84-141; call site scripts/evaluate_M2_ibm.py:136-141).  The reference's
+ * defaults are fixed_smooth 0.8, prob_smooth 0.9, prior 0.5, snr_opt_db 15, n_init 10 (:10-14).  soft / hard are
+ * [F][NP] f32 (either may be NULL): the mask and its threshold at 0.5. */
+int32_t gvn_spp_mask(const gvn_batch* batch /*HOST*/, float fixed_smooth, float prob_smooth, float prior,
+                     float snr_opt_db, int32_t n_init, float* soft, float* hard, void* stream);
+
 /* NMF initialisation W = max(rand, eps), H = max(rand, eps), g = 1, Vb = W@H, from caller
  * supplied uniforms (mcem.py:36-57); also fills padding frames with benign values. */
 int32_t gvn_init_nmf(const gvn_batch* batch /*HOST*/, const float* rand_W /*[B][F][K]*/,

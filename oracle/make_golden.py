@@ -18,6 +18,7 @@ Run from the repo root (the reference tree is read-only, so no bytecode is writt
   ``mcem.py:155-178``), the state after every step is stored, and a second instance is run
   through ``run()`` itself to check that the stepwise drive is the same computation.
 
+* ``spp_mask.npz`` -- ``timo_mask_estimation`` of ``python/models/spp_estimation.py`` on a synthetic mixture.
 * ``mcem_M2_noNMF.npz`` -- the same drive for ``MCEM_M2_noNMF`` (``mcem.py:609-760``).
 
 /root/reference does not exist on the GPU box; only the committed .npz files travel.
@@ -248,6 +249,22 @@ def golden_nonmf(tag="M2_noNMF", L=16, niter=3, chain=(3, 4, 3, 5), T=6144, seed
     print("golden %-8s N=%d L=%d niter=%d steps=%d cost=%s" % (tag, N, L, niter, len(u_), np.round(cost, 4)))
 
 
+def golden_spp():
+    """timo_mask_estimation (python/models/spp_estimation.py:198-218) of the reference on a synthetic mixture."""
+    sys.path.insert(0, REF)
+    for k in [k for k in sys.modules if k == "python" or k.startswith("python.")]:
+        del sys.modules[k]
+    from python.models.spp_estimation import timo_mask_estimation
+    sys.path.remove(REF)
+    from oracle import spp_oracle
+    x, _, _ = synth_utterance(3, seed=2, T=16000)
+    P = (np.abs(stft_oracle.stft(x, **STFT_KW)) ** 2).astype(np.float32)        # evaluate_M2_ibm.py:137 (float32)
+    mask = timo_mask_estimation(P)
+    assert mask.dtype == np.float32 and np.array_equal(spp_oracle.timo_mask(P), mask)
+    np.savez_compressed(os.path.join(OUT, "spp_mask.npz"), x=x, power=P, mask=mask)
+    print("golden spp: %s frames, speech share %.3f" % (P.shape, float((mask > 0.5).mean())))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     golden_stft()
@@ -255,3 +272,4 @@ if __name__ == "__main__":
     golden_mcem("M2_ibm", "M2", "ibm", L=16, K=10, niter=3, chain=(3, 5, 4, 6))
     golden_mcem("M2_vad", "M2", "vad", L=32, K=10, niter=2, chain=(2, 3, 2, 3))
     golden_nonmf()
+    golden_spp()

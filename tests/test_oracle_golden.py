@@ -100,3 +100,13 @@ def test_nonmf_oracle_reproduces_reference_run():
     np.testing.assert_array_equal(seen["Vs0"], g["Vs_E0"])
     np.testing.assert_array_equal(o.S_hat, g["S_hat"])
     np.testing.assert_array_equal(o.N_hat, g["N_hat"])
+
+
+def test_spp_oracle_reproduces_reference_mask():
+    # timo_mask_estimation (python/models/spp_estimation.py:198-218) run by oracle/make_golden.py
+    from oracle import spp_oracle
+    z = np.load(os.path.join(GOLDEN, "spp_mask.npz"))
+    m = spp_oracle.timo_mask(z["power"])
+    assert m.dtype == np.float32
+    np.testing.assert_array_equal(m, z["mask"])
+    assert 0.01 < (m > 0.5).mean() < 0.5
