@@ -326,12 +326,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_estep_tc(const __grid_constant_
         const uint32_t acc_col = (buf ? COL_ACC1 : COL_ACC0) + 16 * half;
         const int nst = (ncol + SROWS - 1) / SROWS;
         float sl = 0.f, sr = 0.f;                          // fp32 inside a chunk (<= 64 pairs), double across chunks
+        int es = 0;                                        // V_FRAC: sum of the unbiased exponents of the pair products
         // one stage = this thread's 16 bins of a 32-row ring box; the accumulator columns of stage s+1
         // are requested from TMEM before the math of stage s (two register sets, statically indexed)
         constexpr bool V_PF = (VAR & 1) != 0;             // prefetch the next stage's accumulator columns
         constexpr bool V_PRE = false;
         constexpr bool V_PROBE = (VAR & 2) != 0;          // probe the next stage's ring barrier before this stage's math
-        constexpr bool V_PACK = (VAR & 4) != 0;           // packed f32x2 arithmetic in the pair loop
+        constexpr bool V_PACK = false;                    // packed f32x2 arithmetic in the pair loop (measured slower, kept for reference)
+        constexpr bool V_FRAC = (VAR & 4) != 0;           // one lg2 + one rcp per 8 pairs: exponent/mantissa split of the pair products
         auto stage = [&](uint32_t (&r)[16], uint32_t (&rn)[16], int s_) {
           const int f0 = c * 128 + s_ * SROWS + 16 * half;
           const uint32_t* xv = nullptr;
@@ -381,6 +383,32 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_estep_tc(const __grid_constant_
                 if (STORE && valid) { st_stream(vo + (2 * j) * 8, v0); st_stream(vo + (2 * j + 1) * 8, v1); }
               }
               sl = acc2.x; sr = acc2.y;
+            } else if (V_FRAC && ENERGY) {
+              // sum_j log(pr_j) = ln2 * (sum_j e_j + lg2(prod_j m_j)) and sum_j qn_j/pr_j = N/P with pr_j = m_j * 2^e_j,
+              // m_j in [1,2): the exponents are summed as integers, the mantissas multiplied (P < 2^8), the quotients
+              // (scaled by 2^-e_j, exact) carried as one fraction N/P -- 2 special-function operations per 8 pairs
+              // instead of 16, paid with integer/FMA-pipe instructions
+              float Pm = 1.f, Nn = 0.f;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float t0 = fmaf(__uint_as_float(r[2 * j]), SC3, b3v[2 * j]), t1 = fmaf(__uint_as_float(r[2 * j + 1]), SC3, b3v[2 * j + 1]);
+                const float v0 = ex2_approx(t0);
+                const float v1 = ex2_approx(t1);
+                const uint32_t w0 = xv[(2 * j) * TM], w1 = xv[(2 * j + 1) * TM];
+                const float a = fmaf(g, v0, __uint_as_float(w0 << 16)), b = fmaf(g, v1, __uint_as_float(w1 << 16));
+                const float pr = a * b;
+                const float qn = fmaf(__uint_as_float(w0), b, __uint_as_float(w1) * a);
+                const uint32_t pb = __float_as_uint(pr);
+                const float m = __uint_as_float((pb & 0x007fffffu) | 0x3f800000u);
+                es += (int)(pb >> 23);
+                const float q = qn * __uint_as_float(0x7f000000u - (pb & 0x7f800000u));       // qn * 2^-e
+                Nn = fmaf(q, Pm, Nn * m);
+                Pm *= m;
+                if (STORE && valid) { st_stream(vo + (2 * j) * 8, v0); st_stream(vo + (2 * j + 1) * 8, v1); }
+              }
+              es -= 127 * 8;
+              sl += lg2_approx(Pm);
+              sr = fmaf(Nn, rcp_approx(Pm), sr);
             } else {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -428,7 +456,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_estep_tc(const __grid_constant_
           stage(ra, rb, s);
           if (s + 1 < nst) stage(V_PF ? rb : ra, ra, s + 1);
         }
-        if (ENERGY) dsum += (double)fmaf(sl, LN2, sr);
+        if (ENERGY) dsum += (double)fmaf(V_FRAC ? sl + (float)es : sl, LN2, sr);
         fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_free + buf);
@@ -619,11 +647,8 @@ int32_t launch_estep_tc(const gvn_batch* b, const void* packed, int burnin, int 
       case 0: return launch_tc<16, false, 0>(mx, a, grid, st);
       case 1: return launch_tc<16, false, 1>(mx, a, grid, st);
       case 2: return launch_tc<16, false, 2>(mx, a, grid, st);
-      case 3: return launch_tc<16, false, 3>(mx, a, grid, st);
-      case 4: return launch_tc<16, false, 4>(mx, a, grid, st);
-      case 5: return launch_tc<16, false, 5>(mx, a, grid, st);
-      case 6: return launch_tc<16, false, 6>(mx, a, grid, st);
-      default: return launch_tc<16, false, 7>(mx, a, grid, st);
+      case 7: return launch_tc<16, false, 7>(mx, a, grid, st);
+      default: return launch_tc<16, false, GVN_TC_DEFAULT_VARIANT>(mx, a, grid, st);
     }
   }
   if (t.L16 == 32) return launch_tc<32, false, GVN_TC_DEFAULT_VARIANT>(mx, a, grid, st);
