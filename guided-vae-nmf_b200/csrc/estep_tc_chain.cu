@@ -48,7 +48,7 @@ constexpr int NEW = NE / 32;            // epilogue warps
 constexpr int NTHREADS = 320;
 constexpr int STAGE_BYTES = SROWS * TM * 4;
 #ifndef GVN_TC_DEFAULT_VARIANT
-#define GVN_TC_DEFAULT_VARIANT 3
+#define GVN_TC_DEFAULT_VARIANT 19
 #endif
 
 // TMEM column map (512 columns allocated)
@@ -62,6 +62,13 @@ __device__ __forceinline__ void bar_epilogue() { asm volatile("bar.sync 1, 256;"
 template <int L16, bool PROF_ON, int VAR>
 __global__ void __launch_bounds__(NTHREADS, 1) k_estep_tc(const __grid_constant__ CUtensorMap tm_xv, TcArgs p) {
   constexpr int K1 = 2 * L16;                             // z hi | z lo against [W1 | W1]
+  // Hidden-layer hand-over in NBLK blocks: the epilogue warps signal every 64/NBLK columns of tanh output, the issuer
+  // starts the next layer's MMA k-steps block by block, so the MMA runs under the rest of the tanh work.  The
+  // second hidden layer then accumulates in output buffer 1 (the first layer's accumulator, aliased to buffer 0,
+  // is still being read when its first k-steps start).
+  constexpr int NBLK = (VAR & 16) ? 4 : ((VAR & 8) ? 2 : 1);
+  constexpr int CPB = 64 / NBLK;                          // columns per block and half
+  constexpr uint32_t COL_ACCH2 = NBLK > 1 ? COL_ACC1 : COL_ACCH;
   extern __shared__ __align__(1024) unsigned char smem[];
   const int F = p.F, FN = p.FN, NP = p.NP, L = p.L;
   const int NCH = (FN + 127) / 128;                       // output-layer chunks (last one may be 16 wide)
@@ -82,7 +89,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_estep_tc(const __grid_constant_
   uint64_t* bar_full = bars + 7;                          // [nstage] TMA -> E
   uint64_t* bar_empty = bars + 7 + MAX_STAGES;            // [nstage] E -> P
   uint64_t* bar_eps = bars + 7 + 2 * MAX_STAGES;          // E(owners) -> E(noise warps): hand-over buffer has been read
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8 + 2 * MAX_STAGES);
+  uint64_t* bar_hb = bars + 8 + 2 * MAX_STAGES;           // [4] E -> M : one 16/32-column block of the hidden activations is in TMEM (NBLK > 1)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12 + 2 * MAX_STAGES);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n0 = blockIdx.x * TM;
@@ -105,6 +113,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_estep_tc(const __grid_constant_
     mbar_init(bar_h, NEW);
     mbar_init(bar_hfull, 1);
     mbar_init(bar_eps, 4);
+    for (int i = 0; i < 4; ++i) mbar_init(bar_hb + i, NEW);
     for (int i = 0; i < 2; ++i) { mbar_init(bar_d + i, 1); mbar_init(bar_free + i, NEW); }
     for (int i = 0; i < p.nstage; ++i) { mbar_init(bar_full + i, 1); mbar_init(bar_empty + i, NEW); }
     mbar_init_fence();
@@ -149,27 +158,53 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_estep_tc(const __grid_constant_
           mma_ts(tbase + COL_ACCH, tbase + COL_Z + k0 / 2, smem_desc(smem_u32(sW1) + (k0 / 8) * 128, lbo, sbo1),
                  idesc_f16(TM, HID), k0 > 0);
         mma_commit(bar_hfull);
-        // layer 2: ACCH = H1(128 x 128) * W2^T
-        mbar_wait_idle(bar_h, n_h++ & 1);
-        fence_after();
+        // layer 2: ACCH2 = H1(128 x 128) * W2^T
+        auto issue_blocks = [&](uint32_t d_col, uint32_t b_base, uint32_t sbo_, uint32_t idesc_) {
 #pragma unroll
-        for (int k0 = 0; k0 < HID; k0 += 16)
-          mma_ts(tbase + COL_ACCH, tbase + COL_A + k0 / 2, smem_desc(smem_u32(sW2) + (k0 / 8) * 128, lbo, sbo),
-                 idesc_f16(TM, HID), k0 > 0);
+          for (int blk = 0; blk < NBLK; ++blk) {
+            mbar_wait_idle(bar_hb + blk, n_h & 1);
+            fence_after();
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+              for (int kk = 0; kk < CPB; kk += 16) {
+                const int k0 = 64 * h + blk * CPB + kk;
+                mma_ts(tbase + d_col, tbase + COL_A + k0 / 2, smem_desc(b_base + (k0 / 8) * 128, lbo, sbo_), idesc_,
+                       !(blk == 0 && h == 0 && kk == 0));
+              }
+          }
+          ++n_h;
+        };
+        if constexpr (NBLK > 1) {
+          issue_blocks(COL_ACCH2, smem_u32(sW2), sbo, idesc_f16(TM, HID));
+        } else {
+          mbar_wait_idle(bar_h, n_h++ & 1);
+          fence_after();
+#pragma unroll
+          for (int k0 = 0; k0 < HID; k0 += 16)
+            mma_ts(tbase + COL_ACCH, tbase + COL_A + k0 / 2, smem_desc(smem_u32(sW2) + (k0 / 8) * 128, lbo, sbo),
+                   idesc_f16(TM, HID), k0 > 0);
+        }
         mma_commit(bar_hfull);
         // layer 3: chunks of the output features, alternating accumulator buffers
-        mbar_wait_idle(bar_h, n_h++ & 1);
-        fence_after();
+        if constexpr (NBLK == 1) {
+          mbar_wait_idle(bar_h, n_h++ & 1);
+          fence_after();
+        }
         for (int c = 0; c < NCH; ++c) {
           const int buf = c & 1, ncol = min(128, FN - c * 128);
           if (buf) mbar_wait_idle(bar_free + 1, (n_free1++ & 1) ^ 1); else mbar_wait_idle(bar_free + 0, (n_free0++ & 1) ^ 1);
           fence_after();
           const uint32_t b0 = smem_u32(sW3) + (uint32_t)(c * 16) * sbo;
           const uint32_t idesc = idesc_f16(TM, ncol);
+          if (NBLK > 1 && c == 0) {                          // first chunk: k-steps follow the blocks of the second tanh layer
+            issue_blocks(COL_ACC0, b0, sbo, idesc);
+          } else {
 #pragma unroll
-          for (int k0 = 0; k0 < HID; k0 += 16)
-            mma_ts(tbase + (buf ? COL_ACC1 : COL_ACC0), tbase + COL_A + k0 / 2, smem_desc(b0 + (k0 / 8) * 128, lbo, sbo),
-                   idesc, k0 > 0);
+            for (int k0 = 0; k0 < HID; k0 += 16)
+              mma_ts(tbase + (buf ? COL_ACC1 : COL_ACC0), tbase + COL_A + k0 / 2, smem_desc(b0 + (k0 / 8) * 128, lbo, sbo),
+                     idesc, k0 > 0);
+          }
           mma_commit(bar_d + buf);
         }
       }
@@ -285,7 +320,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_estep_tc(const __grid_constant_
 #pragma unroll
       for (int c0 = 0; c0 < 64; c0 += 16) {
         uint32_t r[16], bq[16];
-        tmem_ld16(tlane + COL_ACCH + 64 * half + c0, r);
+        tmem_ld16(tlane + (decltype(layer0)::value ? COL_ACCH : COL_ACCH2) + 64 * half + c0, r);
         if constexpr (decltype(layer0)::value) tmem_ld16(tlane + COL_YP + 64 * half + c0, bq);
         tmem_ld_wait();
         uint32_t o[8];
@@ -301,11 +336,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_estep_tc(const __grid_constant_
           o[j] = tanh_f16x2(fmaf(__uint_as_float(r[2 * j]), W_SCALE_INV, b0), fmaf(__uint_as_float(r[2 * j + 1]), W_SCALE_INV, b1));
         }
         tmem_st8(tlane + COL_A + (64 * half + c0) / 2, o);
+        if (NBLK > 1 && (c0 + 16) % CPB == 0) {             // this block of the A operand is complete
+          tmem_st_wait();
+          fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_hb + (c0 + 16) / CPB - 1);
+        }
       }
-      tmem_st_wait();
-      fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_h);
+      if (NBLK == 1) {
+        tmem_st_wait();
+        fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_h);
+      }
       PROF(decltype(layer0)::value ? 2 : 4);
     };
 
@@ -579,7 +622,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_estep_tc(const __grid_constant_
 template <int L16, bool PROF_ON, int VAR>
 int32_t launch_tc(const CUtensorMap& mx, const TcArgs& a, int grid, cudaStream_t st) {
   const size_t fixed = (size_t)HID * 2 * L16 * 2 + (size_t)HID * HID * 2 + (size_t)a.FN * HID * 2 + (size_t)(a.FN + 16 + HID) * 4 +
-                       (size_t)2 * NE * 8 + (8 + 2 * MAX_STAGES) * 8 + 16;
+                       (size_t)2 * NE * 8 + (12 + 2 * MAX_STAGES) * 8 + 16;
   TcArgs args = a;
   const size_t cap = 227 * 1024;
   int nstage = (int)((cap - fixed) / STAGE_BYTES);
@@ -640,14 +683,14 @@ int32_t launch_estep_tc(const gvn_batch* b, const void* packed, int burnin, int 
   a.prof = g_prof;
   const int grid = (b->NP + TM - 1) / TM;
   static int var = -1;                                  // GVN_TC_VARIANT: epilogue scheduling experiments (see `stage`)
-  if (var < 0) { const char* e = getenv("GVN_TC_VARIANT"); var = e ? atoi(e) & 7 : GVN_TC_DEFAULT_VARIANT; }
+  if (var < 0) { const char* e = getenv("GVN_TC_VARIANT"); var = e ? atoi(e) & 31 : GVN_TC_DEFAULT_VARIANT; }
   if (t.L16 == 16) {
     if (a.prof != nullptr) return launch_tc<16, true, GVN_TC_DEFAULT_VARIANT>(mx, a, grid, st);
     switch (var) {
       case 0: return launch_tc<16, false, 0>(mx, a, grid, st);
-      case 1: return launch_tc<16, false, 1>(mx, a, grid, st);
-      case 2: return launch_tc<16, false, 2>(mx, a, grid, st);
-      case 7: return launch_tc<16, false, 7>(mx, a, grid, st);
+      case 3: return launch_tc<16, false, 3>(mx, a, grid, st);
+      case 11: return launch_tc<16, false, 11>(mx, a, grid, st);
+      case 23: return launch_tc<16, false, 23>(mx, a, grid, st);
       default: return launch_tc<16, false, GVN_TC_DEFAULT_VARIANT>(mx, a, grid, st);
     }
   }
