@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_estep_tc(const __grid_constant_
       hidden(std::true_type{});
       hidden(std::false_type{});
       double dsum = 0.0;
-      float* vo = STORE ? vs_out + tile_off(16 * half, n, F) : nullptr;   // column-tile order: bin stride = 8 floats
+      float* vo = STORE ? vs_out + tile_off(16 * half, n, F) : nullptr;   // column-tile order: bin stride = GVN_VS_TILE floats
 #pragma unroll 1
       for (int c = 0; c < NCH; ++c) {
         const int buf = c & 1, ncol = min(128, FN - c * 128);
@@ -393,7 +393,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_estep_tc(const __grid_constant_
             }
           }
           if (V_PF && s_ + 1 < nst) tmem_ld16(tlane + acc_col + (s_ + 1) * SROWS, rn);   // prefetch
-          float* vo = STORE ? vs_out + tile_off(f0, n, F) : nullptr;              // column-tile order: bin stride = 8 floats
+          float* vo = STORE ? vs_out + tile_off(f0, n, F) : nullptr;              // column-tile order: bin stride = GVN_VS_TILE floats
           if (f0 + 16 <= F) {                              // full group: 8 pairs of bins
             float b3v[16];
             uint32_t wv[16];
@@ -423,7 +423,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_estep_tc(const __grid_constant_
                   const float qn = fmaf(__uint_as_float(w0), ab.y, __uint_as_float(w1) * ab.x);
                   acc2 = __ffma2_rn(make_float2(1.0f, qn), make_float2(lg2_approx(pr), rcp_approx(pr)), acc2);
                 }
-                if (STORE && valid) { st_stream(vo + (2 * j) * 8, v0); st_stream(vo + (2 * j + 1) * 8, v1); }
+                if (STORE && valid) { st_stream(vo + (2 * j) * GVN_VS_TILE, v0); st_stream(vo + (2 * j + 1) * GVN_VS_TILE, v1); }
               }
               sl = acc2.x; sr = acc2.y;
             } else if (V_FRAC && ENERGY) {
@@ -447,7 +447,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_estep_tc(const __grid_constant_
                 const float q = qn * __uint_as_float(0x7f000000u - (pb & 0x7f800000u));       // qn * 2^-e
                 Nn = fmaf(q, Pm, Nn * m);
                 Pm *= m;
-                if (STORE && valid) { st_stream(vo + (2 * j) * 8, v0); st_stream(vo + (2 * j + 1) * 8, v1); }
+                if (STORE && valid) { st_stream(vo + (2 * j) * GVN_VS_TILE, v0); st_stream(vo + (2 * j + 1) * GVN_VS_TILE, v1); }
               }
               es -= 127 * 8;
               sl += lg2_approx(Pm);
@@ -466,7 +466,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_estep_tc(const __grid_constant_
                 const float qn = fmaf(__uint_as_float(w0), b, __uint_as_float(w1) * a);      // X2 = the whole word (k_pack_xv)
                 sr = fmaf(qn, rcp_approx(pr), sr);
               }
-              if (STORE && valid) { st_stream(vo + (2 * j) * 8, v0); st_stream(vo + (2 * j + 1) * 8, v1); }
+              if (STORE && valid) { st_stream(vo + (2 * j) * GVN_VS_TILE, v0); st_stream(vo + (2 * j + 1) * GVN_VS_TILE, v1); }
             }
             }
           } else {                                         // ragged tail of the spectrum (F = 513: one bin)
@@ -482,7 +482,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_estep_tc(const __grid_constant_
                 sl += lg2_approx(a);
                 sr = fmaf(__uint_as_float(w0), rcp_approx(a), sr);
               }
-              if (STORE && valid) st_stream(vo + j * 8, v0);
+              if (STORE && valid) st_stream(vo + j * GVN_VS_TILE, v0);
             }
           }
           if (ENERGY) {

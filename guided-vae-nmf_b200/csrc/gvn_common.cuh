@@ -32,8 +32,10 @@ struct DecoderLayout {
 
 __host__ __device__ inline size_t round_up(size_t x, size_t m) { return (x + m - 1) / m * m; }
 
-// column-tile order of Vs / X2t (include/gvn.h): offset of (f, n) inside one [NP/8][F][8] plane
-__host__ __device__ inline size_t tile_off(int f, int n, int F) { return ((size_t)(n >> 3) * F + f) * 8 + (n & 7); }
+// column-tile order of Vs / X2t (include/gvn.h): offset of (f, n) inside one [NP/8][F][8] plane (GVN_VS_TILE = 8)
+__host__ __device__ inline size_t tile_off(int f, int n, int F) {
+  return ((size_t)(n / GVN_VS_TILE) * F + f) * GVN_VS_TILE + (n % GVN_VS_TILE);
+}
 
 // Tensor-core operand image (estep_tc.cu): f16 hi and lo planes of W1z (K padded to 16),
 // W2 and W3 (N padded to a multiple of 16) in the canonical no-swizzle K-major UMMA layout.

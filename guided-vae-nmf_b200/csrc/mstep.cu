@@ -114,7 +114,8 @@ __global__ void __launch_bounds__(256) k_mstep_cols(int F, int K, int NP, int R,
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile = blockIdx.x, gn = tile * MS_TILE + lane;
   const int b = frame_utt[tile * MS_TILE];
-  if (threadIdx.x < 4) cost_part[tile * 4 + threadIdx.x] = 0.f;     // cost_part is indexed by GVN_COST_TILE (8) frames
+  constexpr int CPT = MS_TILE / GVN_COST_TILE;                      // cost_part entries per 32-frame tile
+  if (threadIdx.x < CPT) cost_part[tile * CPT + threadIdx.x] = 0.f;
   if (b < 0) return;
   const bool valid = frame_utt[gn] >= 0;
   const float* wb = Wun + (size_t)b * F * K;
@@ -220,7 +221,7 @@ __global__ void __launch_bounds__(256) k_mstep_cols(int F, int K, int NP, int R,
   if (threadIdx.x == 0) {
     float s = 0.f;
     for (int w = 0; w < MS_WARPS; ++w) s += red1[w];
-    cost_part[tile * 4] = s;
+    cost_part[tile * CPT] = s;
   }
   // normalised H (mcem.py:133) and new g
   if (warp == 0 && valid) {

@@ -13,7 +13,8 @@ namespace gvn {
 namespace {
 
 constexpr int NB = GVN_COST_TILE;
-constexpr int GT = 256;               // 32 frequency lanes x 8 frames
+constexpr int GT = 256;               // GFL frequency lanes x NB frames
+constexpr int GFL = GT / NB;
 
 __device__ __forceinline__ float rcp_fast(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float lg2_fast(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -26,13 +27,13 @@ __global__ void __launch_bounds__(GT) k_gain_cols(int F, int NP, int R, int ntil
   __shared__ float wts[GVN_MAX_R_SLOTS][NB];
   __shared__ float misc[8];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int n = tid & (NB - 1), fl = tid >> 3;
+  const int n = tid & (NB - 1), fl = tid / NB;
   const size_t slab = (size_t)(NP / NB) * F * NB;           // one sample slot
   for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
     const int gn = t * NB + n;
     if (frame_utt[(size_t)t * NB] < 0) { if (tid == 0) cost_part[t] = 0.f; continue; }   // tiles never straddle utterances
     __syncthreads();                                        // previous tile is done with the shared arrays
-    for (int i = tid; i < R * NB; i += GT) wts[i >> 3][i & 7] = Vs_w[(size_t)(i >> 3) * NP + t * NB + (i & 7)];
+    for (int i = tid; i < R * NB; i += GT) wts[i / NB][i % NB] = Vs_w[(size_t)(i / NB) * NP + t * NB + (i % NB)];
     __syncthreads();
     const bool valid = frame_utt[gn] >= 0;
     const float gg = g[gn];
@@ -41,7 +42,7 @@ __global__ void __launch_bounds__(GT) k_gain_cols(int F, int NP, int R, int ntil
 
     // ---------------- gain update (mcem.py:566-576)
     float ng = 0.f, dg = 0.f;
-    for (int f = fl; f < F; f += 32) {
+    for (int f = fl; f < F; f += GFL) {
       const float vb = Vb[(size_t)f * NP + gn];
       const float* vs = vs0 + (size_t)f * NB;
       float t1 = 0.f, t2 = 0.f;
@@ -64,10 +65,11 @@ __global__ void __launch_bounds__(GT) k_gain_cols(int F, int NP, int R, int ntil
       ng = fmaf(__ldg(x2p + (size_t)f * NB), t2, ng);
       dg += t1;
     }
-    ng += __shfl_xor_sync(0xffffffffu, ng, 8);
-    ng += __shfl_xor_sync(0xffffffffu, ng, 16);
-    dg += __shfl_xor_sync(0xffffffffu, dg, 8);
-    dg += __shfl_xor_sync(0xffffffffu, dg, 16);
+#pragma unroll
+    for (int o = NB; o < 32; o <<= 1) {                     // lanes that share the frame n
+      ng += __shfl_xor_sync(0xffffffffu, ng, o);
+      dg += __shfl_xor_sync(0xffffffffu, dg, o);
+    }
     if (lane < NB) { red[warp][0][lane] = ng; red[warp][1][lane] = dg; }
     __syncthreads();
     float sn = 0.f, sd = 0.f;
@@ -78,7 +80,7 @@ __global__ void __launch_bounds__(GT) k_gain_cols(int F, int NP, int R, int ntil
 
     // ---------------- cost with the new gain (mcem.py:585-588, :530-532)
     float cl = 0.f, cr = 0.f;
-    for (int f = fl; f < F; f += 32) {
+    for (int f = fl; f < F; f += GFL) {
       const float vb = Vb[(size_t)f * NP + gn];
       const float* vs = vs0 + (size_t)f * NB;
       float sl = 0.f, sr = 0.f;

@@ -8,6 +8,7 @@ LIB_PATH = os.path.join(os.path.dirname(_HERE), "libgvn.so")
 
 GVN_FRAME_ALIGN = 32
 GVN_HIDDEN = 128
+GVN_VS_TILE = 8
 GVN_COST_TILE = 8
 GVN_MAX_K = 32
 GVN_MAX_L = 64

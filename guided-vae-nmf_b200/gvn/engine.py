@@ -147,8 +147,9 @@ class Batch:
         self.g = torch.ones(NP, **f32)
         self.Vb = torch.ones(F, NP, **f32)
         self.Z = torch.zeros(L, NP, **f32)
-        self.Vs = torch.zeros(R_cap, NP // 8, F, 8, **f32)  # slot form in column-tile order, see include/gvn.h
-        self.X2t = torch.ones(NP // 8, F, 8, **f32)
+        VT = _lib.GVN_VS_TILE
+        self.Vs = torch.zeros(R_cap, NP // VT, F, VT, **f32)  # slot form in column-tile order, see include/gvn.h
+        self.X2t = torch.ones(NP // VT, F, VT, **f32)
         self.Vs_w = torch.zeros(R_cap, NP, **f32)
         self.XV = torch.empty(F, NP, dtype=torch.int32, device=device)
         self.yproj = torch.zeros(GVN_HIDDEN, NP, **f32)
@@ -192,7 +193,8 @@ class Batch:
     def set_samples(self, vs, w=None):
         """(R,F,NP) sample tensor -> the column-tile slot form (tests)."""
         R = vs.shape[0]
-        self.Vs[:R].copy_(vs.reshape(R, self.F, self.NP // 8, 8).permute(0, 2, 1, 3))
+        VT = _lib.GVN_VS_TILE
+        self.Vs[:R].copy_(vs.reshape(R, self.F, self.NP // VT, VT).permute(0, 2, 1, 3))
         self.Vs_w[:R].copy_(torch.ones(R, self.NP, device=vs.device) if w is None else w)
 
 

@@ -263,7 +263,7 @@ class EM_noNMF(EM):
             Xt = np.ascontiguousarray(X.T.astype(np.complex64))
             b.Xc[:, b.cols(0), :] = torch.from_numpy(Xt.view(np.float32).reshape(F, N, 2)).to(dev)
             b.scatter_cols(b.X2, [torch.from_numpy((np.abs(X.T) ** 2).astype(np.float32))])       # mcem.py:505
-            b.X2t.copy_(b.X2.reshape(F, b.NP // 8, 8).permute(1, 0, 2))
+            b.X2t.copy_(b.X2.reshape(F, b.NP // b.X2t.shape[2], b.X2t.shape[2]).permute(1, 0, 2))
             b.scatter_cols(b.Vb, [torch.as_tensor(np.asarray(c["Vb"]).T).to(**f32)])              # :508
             b.scatter_cols(b.g, [torch.as_tensor(c["g"]).to(**f32).reshape(-1)])                  # :509
             b.scatter_cols(b.Z, [torch.t(torch.as_tensor(Z).to(**f32))])                          # :623

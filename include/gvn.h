@@ -61,7 +61,8 @@ extern "C" {
 
 #define GVN_VERSION 100
 #define GVN_FRAME_ALIGN 32      /* utterances start on multiples of this many frames   */
-#define GVN_COST_TILE 8        /* frames per partial cost sum written by gvn_mstep       */
+#define GVN_VS_TILE 8          /* frames per column block of Vs / X2t                    */
+#define GVN_COST_TILE 8        /* frames per partial cost sum written by gvn_mstep (= GVN_VS_TILE) */
 #define GVN_HIDDEN 128          /* decoder hidden width (h_dim=[128,128] in every script) */
 #define GVN_MAX_K 32            /* NMF rank limit */
 #define GVN_MAX_L 64            /* latent dimension limit */
