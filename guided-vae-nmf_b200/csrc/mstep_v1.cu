@@ -166,7 +166,7 @@ template <int KMAX, int RT>
 __global__ void __launch_bounds__(WT, (KMAX > 16 ? 1 : 2)) k_w_v2(int F, int K, int NP, int R_rt, int ws, const int32_t* __restrict__ frame_off,
                                                 const int32_t* __restrict__ n_frames, const float* __restrict__ X2t,
                                                 const float* __restrict__ Vs, const float* __restrict__ Mt,
-                                                const float* __restrict__ W, float* __restrict__ Wun) {
+                                                const float* __restrict__ W, float* __restrict__ Wun, float* __restrict__ Wpart) {
   extern __shared__ __align__(128) float smw[];             // [WS][stage]
   __shared__ __align__(8) uint64_t full[WS], empty[WS];
   const int R = RT > 0 ? RT : R_rt;
@@ -174,7 +174,12 @@ __global__ void __launch_bounds__(WT, (KMAX > 16 ? 1 : 2)) k_w_v2(int F, int K, 
   const int b = blockIdx.y, f0 = blockIdx.x * WROWS;
   const int rows = min(WROWS, F - f0);
   const int n_begin = frame_off[b], N = n_frames[b];
-  const int ntile = (N + NB - 1) / NB, t0 = n_begin / NB, T8 = NP / NB;
+  // blockIdx.z splits the frames of the utterance (few long utterances would otherwise leave most SMs idle): this
+  // CTA sweeps tiles [tb, te) and, when split, leaves its partial sums in Wpart for k_w_finish
+  const int ntile_all = (N + NB - 1) / NB, nsplit = gridDim.z;
+  const int per_split = (ntile_all + nsplit - 1) / nsplit;
+  const int tb = min((int)blockIdx.z * per_split, ntile_all), te = min(tb + per_split, ntile_all);
+  const int ntile = te - tb, t0 = n_begin / NB + tb, T8 = NP / NB;
   constexpr int PSt = WROWS * NB;                           // plane stride inside a stage (floats)
   const int MO = (R + 1) * PSt;                             // offset of the column data inside a stage
   const int MR = K + 1 + R;
@@ -234,7 +239,7 @@ __global__ void __launch_bounds__(WT, (KMAX > 16 ? 1 : 2)) k_w_v2(int F, int K, 
         if (r < R) single_acc(gg, vb, vs[r * PSt], wt[r * NB], s1, s2);
       }
       float a = vs[R * PSt] * s2;
-      if (ti * NB + n >= N) { a = 0.f; s1 = 0.f; }          // padding frames of the last tile contribute nothing
+      if ((tb + ti) * NB + n >= N) { a = 0.f; s1 = 0.f; }   // padding frames of the last tile contribute nothing
 #pragma unroll
       for (int k = 0; k < KMAX; ++k) if (k < K) { const float h = mt[k * NB]; num[k] = fmaf(a, h, num[k]); den[k] = fmaf(s1, h, den[k]); }
     }
@@ -251,9 +256,31 @@ __global__ void __launch_bounds__(WT, (KMAX > 16 ? 1 : 2)) k_w_v2(int F, int K, 
     }
   }
   if (n == 0 && rowok) {
+    if (nsplit == 1) {
 #pragma unroll
-    for (int k = 0; k < KMAX; ++k)
-      if (k < K) Wun[((size_t)b * F + f) * K + k] = w[k] * sqrtf(num[k] / den[k]);
+      for (int k = 0; k < KMAX; ++k)
+        if (k < K) Wun[((size_t)b * F + f) * K + k] = w[k] * sqrtf(num[k] / den[k]);
+    } else {
+      float* dst = Wpart + ((((size_t)b * nsplit + blockIdx.z) * F + f) * K) * 2;
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k)
+        if (k < K) { dst[2 * k] = num[k]; dst[2 * k + 1] = den[k]; }
+    }
+  }
+}
+
+// W <- W * sqrt(sum_z num / sum_z den) from the partial sums of a frame-split W sweep (fixed summation order)
+__global__ void __launch_bounds__(256) k_w_finish(int B, int F, int K, int nsplit, const float* __restrict__ W,
+                                                  const float* __restrict__ Wpart, float* __restrict__ Wun) {
+  const size_t total = (size_t)B * F * K;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t b = i / ((size_t)F * K), fk = i - b * F * K;
+    float nu = 0.f, de = 0.f;
+    for (int z = 0; z < nsplit; ++z) {
+      const float2 v = *reinterpret_cast<const float2*>(Wpart + (((b * nsplit + z) * F * K) + fk) * 2);
+      nu += v.x; de += v.y;
+    }
+    Wun[i] = W[i] * sqrtf(nu / de);
   }
 }
 
@@ -832,8 +859,21 @@ int32_t launch_cols(const ColsArgs& a, size_t smem, int grid, cudaStream_t st) {
   return check_launch("k_cols_v1");
 }
 
+// Frame split of the W sweep: as many CTAs as the chip holds at once (one per SM for K > 16, else two) when the
+// batch has few, long utterances; every split keeps at least 8 tiles.  Depends only on the batch shape, so the
+// workspace can be sized from it.
+inline int w_nsplit(const gvn_batch* b) {
+  const int row_blocks = (b->F + WROWS - 1) / WROWS;
+  const int slots = 148 * (b->K > 16 ? 1 : 2);
+  const int tiles = b->NP / NB / b->B;                   // average tiles per utterance
+  int ns = slots / (row_blocks * b->B);
+  if (ns > tiles / 8) ns = tiles / 8;
+  if (ns > 16) ns = 16;
+  return ns < 1 ? 1 : ns;
+}
+
 template <int KMAX, int RT>
-int32_t launch_w(const gvn_batch* b, int R, const float* Mt, cudaStream_t st) {
+int32_t launch_w(const gvn_batch* b, int R, const float* Mt, float* Wpart, cudaStream_t st) {
   const size_t stage = (size_t)w_stage_floats(b->K, R) * 4;
   const size_t budget = (KMAX > 16 || 2 * stage > 100 * 1024 ? 200 : 100) * 1024;    // one or two CTAs per SM
   int ws = (int)(budget / stage);
@@ -846,9 +886,14 @@ int32_t launch_w(const gvn_batch* b, int R, const float* Mt, cudaStream_t st) {
     if (e != cudaSuccess) return fail(GVN_E_CUDA, "k_w_v2 smem attr (%zu B): %s", smem, cudaGetErrorString(e));
     smem_set = smem;
   }
-  dim3 gw((b->F + WROWS - 1) / WROWS, b->B);
-  k_w_v2<KMAX, RT><<<gw, WT, smem, st>>>(b->F, b->K, b->NP, R, ws, b->frame_off, b->n_frames, b->X2t, b->Vs, Mt, b->W, b->Wun);
-  return check_launch("k_w_v2");
+  const int nsplit = w_nsplit(b);
+  dim3 gw((b->F + WROWS - 1) / WROWS, b->B, nsplit);
+  k_w_v2<KMAX, RT><<<gw, WT, smem, st>>>(b->F, b->K, b->NP, R, ws, b->frame_off, b->n_frames, b->X2t, b->Vs, Mt, b->W, b->Wun, Wpart);
+  int32_t rc = check_launch("k_w_v2");
+  if (rc || nsplit == 1) return rc;
+  const size_t total = (size_t)b->B * b->F * b->K;
+  k_w_finish<<<(unsigned)((total + 255) / 256 < 592 ? (total + 255) / 256 : 592), 256, 0, st>>>(b->B, b->F, b->K, nsplit, b->W, Wpart, b->Wun);
+  return check_launch("k_w_finish");
 }
 
 inline int kmax_of(int K) { return (K + 3) / 4 * 4; }
@@ -856,7 +901,8 @@ inline int ks_of(int K) { int ks = kmax_of(K); return (ks % 16 == 0) ? ks + 4 : 
 
 template <int KMAX>
 int32_t launch_v1_k(const gvn_batch* b, int R, const ColsArgs& a, size_t smem, int grid, cudaStream_t st) {
-  int32_t rc = R == 10 ? launch_w<KMAX, 10>(b, R, a.Mt, st) : launch_w<KMAX, 0>(b, R, a.Mt, st);
+  float* Wpart = const_cast<float*>(a.Mt) + (size_t)(b->K + 1 + b->R_cap) * b->NP;     // behind the column data (mstep_v1_workspace_bytes)
+  int32_t rc = R == 10 ? launch_w<KMAX, 10>(b, R, a.Mt, Wpart, st) : launch_w<KMAX, 0>(b, R, a.Mt, Wpart, st);
   if (rc) return rc;
   return R == 10 ? launch_cols<KMAX, 10>(a, smem, grid, st) : launch_cols<KMAX, 0>(a, smem, grid, st);
 }
@@ -881,8 +927,11 @@ bool mstep_v1_supported(const gvn_batch* b, int R) {
   return 2 * wstage <= 200 * 1024 && gen_smem_floats(b->F, ks_gen(b->K), b->K, R) * 4 <= 227 * 1024;
 }
 
-// workspace of variant 1: the column data in tile order
-size_t mstep_v1_workspace_bytes(const gvn_batch* b) { return (size_t)(b->K + 1 + b->R_cap) * b->NP * sizeof(float); }
+// workspace of variant 1: the column data in tile order + the partial sums of a frame-split W sweep
+size_t mstep_v1_workspace_bytes(const gvn_batch* b) {
+  const int ns = w_nsplit(b);
+  return ((size_t)(b->K + 1 + b->R_cap) * b->NP + (ns > 1 ? (size_t)b->B * ns * b->F * b->K * 2 : 0)) * sizeof(float);
+}
 
 int32_t launch_mstep_v1(const gvn_batch* b, int R, float* cost_part, float* Mt, cudaStream_t st) {
   k_tile_meta<<<148, 256, 0, st>>>(b->K, R, b->NP, b->H, b->g, b->Vs_w, Mt);
@@ -916,7 +965,8 @@ int32_t launch_mstep_v1(const gvn_batch* b, int R, float* cost_part, float* Mt, 
     }
   }
   // generic shapes: bulk-copy W sweep (runtime R) + L2-resident column sweep
-  rc = b->K <= 16 ? launch_w<16, 0>(b, R, Mt, st) : launch_w<32, 0>(b, R, Mt, st);
+  float* Wpart = Mt + (size_t)(b->K + 1 + b->R_cap) * b->NP;
+  rc = b->K <= 16 ? launch_w<16, 0>(b, R, Mt, Wpart, st) : launch_w<32, 0>(b, R, Mt, Wpart, st);
   if (rc) return rc;
   GenArgs a;
   a.F = b->F; a.K = b->K; a.KS = ks_gen(b->K); a.NP = b->NP; a.R = R; a.ntiles = ntiles;

@@ -34,7 +34,9 @@ def _random_batch(n_frames, F, K, L, R, seed):
 @pytest.mark.parametrize("n_frames,F,K,R", [([251, 100, 37, 256], 513, 10, 10), ([64], 513, 12, 9), ([40, 33], 257, 4, 3),
                                             ([251] * 6, 513, 10, 10), ([70], 129, 1, 2),
                                             # shapes of the generic column sweep: K = 32 (config 4), R = 30 (MCEM_M1's E chain), odd sizes
-                                            ([251, 90], 513, 32, 10), ([251], 513, 10, 30), ([100, 37], 257, 20, 5), ([64], 513, 16, 10)])
+                                            ([251, 90], 513, 32, 10), ([251], 513, 10, 30), ([100, 37], 257, 20, 5), ([64], 513, 16, 10),
+                                            # few long utterances: the W sweep splits the frame axis across CTAs (ragged split included)
+                                            ([1876], 513, 32, 10), ([1000, 640], 513, 10, 10), ([251], 513, 10, 10), ([700, 90, 333], 129, 7, 4)])
 def test_mstep_v1_matches_v0(n_frames, F, K, R):
     from gvn import engine as E
     out = {}
