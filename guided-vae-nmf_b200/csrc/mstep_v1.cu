@@ -212,6 +212,87 @@ __global__ void __launch_bounds__(WT, (KMAX > 16 ? 1 : 2)) k_w_v2(int F, int K, 
   // ================= compute warps =================
   const int n = tid & (NB - 1), rl = tid >> 3, f = f0 + rl;
   const bool rowok = rl < rows;
+  if constexpr (KMAX > 16) {
+    // Large ranks: a thread cannot carry 2*K accumulators.  Phase 1, thread = (row, frame): a = X2 * s2 and s1 of its
+    // point; the four rows of a warp exchange them through 256 bytes of shared memory.  Phase 2, the same warp
+    // regrouped as (row, group of KMAX/8 dictionary columns): num/den of those columns summed over the 8 frames of
+    // the stage -- four (KMAX = 32) accumulator pairs per thread, already reduced over frames.
+    __shared__ __align__(16) float xch[WCT / 32][2][4][NB];
+    constexpr int KG = KMAX / 8;                            // dictionary columns per thread in phase 2
+    const int wi = tid >> 5, rw = lane >> 3, kg = lane & 7;
+    float w[KMAX], num[KG], den[KG];
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) w[k] = (k < K && rowok) ? W[((size_t)b * F + f) * K + k] : 0.f;
+#pragma unroll
+    for (int i = 0; i < KG; ++i) num[i] = den[i] = 0.f;
+    for (int ti = 0; ti < ntile; ++ti) {
+      const int s = ti % ws;
+      mbar_wait(full + s, (ti / ws) & 1);
+      const float* st = smw + (size_t)s * SSt;
+      const float* mt0 = st + MO;
+      float a = 0.f, s1 = 0.f;
+      if (rowok) {
+        const float* vs = st + rl * NB + n;
+        const float* mt = mt0 + n;
+        float vb0 = 0.f, vb1 = 0.f;
+#pragma unroll
+        for (int k = 0; k < KMAX; k += 2) {                   // rows beyond K of the column data are not H
+          if (k < K) vb0 = fmaf(w[k], mt[k * NB], vb0);
+          if (k + 1 < K) vb1 = fmaf(w[k + 1], mt[(k + 1) * NB], vb1);
+        }
+        const float vb = vb0 + vb1, gg = mt[K * NB];
+        const float* wt = mt + (K + 1) * NB;
+        float s2 = 0.f;
+        int r = 0;
+        for (; r + 1 < R; r += 2) pair_acc(gg, vb, vs[r * PSt], vs[(r + 1) * PSt], wt[r * NB], wt[(r + 1) * NB], s1, s2);
+        if (r < R) single_acc(gg, vb, vs[r * PSt], wt[r * NB], s1, s2);
+        a = vs[R * PSt] * s2;
+        if ((tb + ti) * NB + n >= N) { a = 0.f; s1 = 0.f; }
+      }
+      __syncwarp();                                         // phase 2 of the previous stage has read the exchange area
+      xch[wi][0][rw][n] = a;
+      xch[wi][1][rw][n] = s1;
+      __syncwarp();
+      float av[NB], sv[NB];
+#pragma unroll
+      for (int j4 = 0; j4 < NB; j4 += 4) {
+        const float4 t0_ = *reinterpret_cast<const float4*>(&xch[wi][0][rw][j4]), t1_ = *reinterpret_cast<const float4*>(&xch[wi][1][rw][j4]);
+        av[j4] = t0_.x; av[j4 + 1] = t0_.y; av[j4 + 2] = t0_.z; av[j4 + 3] = t0_.w;
+        sv[j4] = t1_.x; sv[j4 + 1] = t1_.y; sv[j4 + 2] = t1_.z; sv[j4 + 3] = t1_.w;
+      }
+#pragma unroll
+      for (int i = 0; i < KG; ++i) {
+        const int k = kg * KG + i;
+        if (k < K) {
+          const float* hp = mt0 + k * NB;                   // H[k][0..7] of the stage
+#pragma unroll
+          for (int j4 = 0; j4 < NB; j4 += 4) {
+            const float4 h = *reinterpret_cast<const float4*>(hp + j4);
+            num[i] = fmaf(av[j4], h.x, fmaf(av[j4 + 1], h.y, fmaf(av[j4 + 2], h.z, fmaf(av[j4 + 3], h.w, num[i]))));
+            den[i] = fmaf(sv[j4], h.x, fmaf(sv[j4 + 1], h.y, fmaf(sv[j4 + 2], h.z, fmaf(sv[j4 + 3], h.w, den[i]))));
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty + s);                // this warp is done with stage s
+    }
+    const int f2_ = f0 + (wi * 4 + rw);                     // the row this lane holds sums for
+    if (wi * 4 + rw < rows) {
+#pragma unroll
+      for (int i = 0; i < KG; ++i) {
+        const int k = kg * KG + i;
+        if (k < K) {
+          if (nsplit == 1) {
+            Wun[((size_t)b * F + f2_) * K + k] = W[((size_t)b * F + f2_) * K + k] * sqrtf(num[i] / den[i]);
+          } else {
+            float* dst = Wpart + ((((size_t)b * nsplit + blockIdx.z) * F + f2_) * K) * 2;
+            dst[2 * k] = num[i]; dst[2 * k + 1] = den[i];
+          }
+        }
+      }
+    }
+    return;
+  }
   float w[KMAX], num[KMAX], den[KMAX];
 #pragma unroll
   for (int k = 0; k < KMAX; ++k) { w[k] = (k < K && rowok) ? W[((size_t)b * F + f) * K + k] : 0.f; num[k] = den[k] = 0.f; }
