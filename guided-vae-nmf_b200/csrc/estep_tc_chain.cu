@@ -630,7 +630,8 @@ int32_t launch_tc(const CUtensorMap& mx, const TcArgs& a, int grid, cudaStream_t
   if (nstage < 2) return fail(GVN_E_UNSUPPORTED_SHAPE, "tensor-core E-step: shared memory does not fit (F=%d L=%d)", a.F, a.L);
   args.nstage = nstage;
   const size_t smem = fixed + (size_t)nstage * STAGE_BYTES;
-  static size_t smem_set = 0;                           // the attribute is sticky: set it once per size
+  static size_t smem_tab[GVN_MAX_DEVICES] = {0};
+  size_t& smem_set = *per_device_slot(smem_tab);                           // the attribute is sticky: set it once per size
   if (smem_set != smem) {
     cudaError_t e = cudaFuncSetAttribute(k_estep_tc<L16, PROF_ON, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(GVN_E_CUDA, "estep_tc smem attr (%zu B): %s", smem, cudaGetErrorString(e));

@@ -19,6 +19,15 @@ int32_t check_launch(const char* what);
 #define GVN_REQUIRE(cond, code, ...) \
   do { if (!(cond)) return ::gvn::fail((code), __VA_ARGS__); } while (0)
 
+// Function attributes (cudaFuncAttributeMaxDynamicSharedMemorySize) are per DEVICE and sticky: launchers remember the
+// value they have set in a table indexed by the current device, so a process that drives several GPUs sets it on each.
+constexpr int GVN_MAX_DEVICES = 64;
+inline size_t* per_device_slot(size_t (&table)[GVN_MAX_DEVICES]) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return &table[dev & (GVN_MAX_DEVICES - 1)];
+}
+
 // ---------------------------------------------------------------------------------------
 // packed decoder image: offsets (in floats) of the fp32 section, computed from the dims
 // ---------------------------------------------------------------------------------------

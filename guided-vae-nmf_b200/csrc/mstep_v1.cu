@@ -918,7 +918,8 @@ __global__ void __launch_bounds__(GT, 2) k_cols_gen(GenArgs p) {
 
 template <int KMAX>
 int32_t launch_cols_gen(const GenArgs& a, size_t smem, int grid, cudaStream_t st) {
-  static size_t smem_set = 0;
+  static size_t smem_tab[GVN_MAX_DEVICES] = {0};
+  size_t& smem_set = *per_device_slot(smem_tab);
   if (smem_set != smem) {
     cudaError_t e = cudaFuncSetAttribute(k_cols_gen<KMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(GVN_E_CUDA, "k_cols_gen smem attr (%zu B): %s", smem, cudaGetErrorString(e));
@@ -930,7 +931,8 @@ int32_t launch_cols_gen(const GenArgs& a, size_t smem, int grid, cudaStream_t st
 
 template <int KMAX, int RT>
 int32_t launch_cols(const ColsArgs& a, size_t smem, int grid, cudaStream_t st) {
-  static size_t smem_set = 0;
+  static size_t smem_tab[GVN_MAX_DEVICES] = {0};
+  size_t& smem_set = *per_device_slot(smem_tab);
   if (smem_set != smem) {
     cudaError_t e = cudaFuncSetAttribute(k_cols_v1<KMAX, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(GVN_E_CUDA, "k_cols_v1 smem attr (%zu B): %s", smem, cudaGetErrorString(e));
@@ -961,7 +963,8 @@ int32_t launch_w(const gvn_batch* b, int R, const float* Mt, float* Wpart, cudaS
   if (ws > WS) ws = WS;
   if (ws < 2) return fail(GVN_E_UNSUPPORTED_SHAPE, "M-step W sweep: a ring stage of %zu bytes does not fit (R=%d)", stage, R);
   const size_t smem = (size_t)ws * stage;
-  static size_t smem_set = 0;
+  static size_t smem_tab[GVN_MAX_DEVICES] = {0};
+  size_t& smem_set = *per_device_slot(smem_tab);
   if (smem_set != smem) {
     cudaError_t e = cudaFuncSetAttribute(k_w_v2<KMAX, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(GVN_E_CUDA, "k_w_v2 smem attr (%zu B): %s", smem, cudaGetErrorString(e));

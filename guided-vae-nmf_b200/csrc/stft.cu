@@ -198,7 +198,8 @@ int32_t launch_stft_power(const gvn_batch* b, const float* wav, int T_stride, co
   GVN_REQUIRE(bits >= 4 && bits <= 11, GVN_E_UNSUPPORTED_SHAPE, "n_fft=%d must be a power of two in [16,2048]", n_fft);
   GVN_REQUIRE(b->F == n_fft / 2 + 1, GVN_E_INVALID, "F=%d does not match n_fft=%d", b->F, n_fft);
   const size_t smem = ((size_t)FPB * n_fft + n_fft / 2) * sizeof(float2);
-  static size_t smem_set = 0;
+  static size_t smem_tab[GVN_MAX_DEVICES] = {0};
+  size_t& smem_set = *per_device_slot(smem_tab);
   if (smem > smem_set) {
     cudaError_t e = cudaFuncSetAttribute(k_stft_power, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(GVN_E_CUDA, "k_stft_power smem attr: %s", cudaGetErrorString(e));
@@ -220,7 +221,8 @@ int32_t launch_istft(const gvn_batch* b, const float* S, int n_fft, int hop, con
   GVN_REQUIRE(b->F == n_fft / 2 + 1, GVN_E_INVALID, "F=%d does not match n_fft=%d", b->F, n_fft);
   float* ws = reinterpret_cast<float*>(workspace);
   const size_t smem = ((size_t)FPB * n_fft + n_fft / 2) * sizeof(float2);
-  static size_t smem_set = 0;
+  static size_t smem_tab[GVN_MAX_DEVICES] = {0};
+  size_t& smem_set = *per_device_slot(smem_tab);
   if (smem > smem_set) {
     cudaError_t e = cudaFuncSetAttribute(k_istft_frames, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(GVN_E_CUDA, "k_istft_frames smem attr: %s", cudaGetErrorString(e));
