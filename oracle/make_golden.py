@@ -18,6 +18,8 @@ Run from the repo root (the reference tree is read-only, so no bytecode is writt
   ``mcem.py:155-178``), the state after every step is stored, and a second instance is run
   through ``run()`` itself to check that the stepwise drive is the same computation.
 
+* ``mcem_M2_vad_wsj0.npz`` -- a slice of the reference's own WSJ0 fixture (mixture = speech + noise) enhanced by the
+  unmodified ``MCEM_M2`` with ``clean_speech_VAD`` labels, scored by the reference's ``python/metrics.py``.
 * ``spp_mask.npz`` -- ``timo_mask_estimation`` of ``python/models/spp_estimation.py`` on a synthetic mixture.
 * ``mcem_M2_noNMF.npz`` -- the same drive for ``MCEM_M2_noNMF`` (``mcem.py:609-760``).
 
@@ -249,6 +251,55 @@ def golden_nonmf(tag="M2_noNMF", L=16, niter=3, chain=(3, 4, 3, 5), T=6144, seed
     print("golden %-8s N=%d L=%d niter=%d steps=%d cost=%s" % (tag, N, L, niter, len(u_), np.round(cost, 4)))
 
 
+def golden_real(tag="M2_vad_wsj0", L=16, K=8, niter=3, chain=(4, 6, 5, 8), start=24000, T=12288):
+    """A slice of the reference's own WSJ0 fixture (data/subset/pickle/CSR-1-WSJ-0/si_et_05_{mixture,speech,noise}-505.p,
+    x = s + n) enhanced by the UNMODIFIED reference: MCEM_M2 guided by clean_speech_VAD labels (target.py:29-50), then
+    SI-SDR / SI-SIR / SI-SAR by the reference's python/metrics.py.  Real speech, real noise, reference code end to end
+    (only the STFT/ISTFT are the restatement: librosa is not installed)."""
+    ref_mcem, ref_models = _reference_modules()
+    sys.path.insert(0, REF)
+    from python.processing.target import clean_speech_VAD
+    from python.metrics import energy_ratios
+    sys.path.remove(REF)
+    x = _load("si_et_05_mixture-505.p")[0][start:start + T].astype(np.float64)
+    sp = _load("si_et_05_speech-505.p")[0][start:start + T].astype(np.float64)
+    no = _load("si_et_05_noise-505.p")[0][start:start + T].astype(np.float64)
+    assert np.max(np.abs(x - sp - no)) < 1e-12
+    X = stft_oracle.stft(x, **STFT_KW).T
+    N, F = X.shape
+    y_np = clean_speech_VAD(stft_oracle.stft(sp, **STFT_KW), quantile_fraction=0.999, quantile_weight=0.999)   # (1, N)
+    y = torch.from_numpy(y_np.T.copy())
+    torch.manual_seed(3)
+    vae = ref_models.DeepGenerativeModel([F, 1, L, [128, 128]], None).eval()
+    for p_ in vae.parameters():
+        p_.requires_grad = False
+    with torch.no_grad():
+        # no trained weights ship with the reference: give the random decoder the long-term spectrum of the clean speech
+        # as its output bias, so that the Wiener filter has a speech model of the right scale
+        S_pow = np.abs(stft_oracle.stft(sp, **STFT_KW)) ** 2
+        vae.decoder.reconstruction.bias.copy_(torch.from_numpy(np.log(S_pow.mean(1) + 1e-8).astype(np.float32)))
+        vae.decoder.hidden[0].bias.normal_(0, 0.3)
+        vae.decoder.hidden[1].bias.normal_(0, 0.3)
+    tape = NoiseTape(seed=99)
+    ref_mcem.torch = _TorchProxy(tape)
+    nE, bE, nW, bW = chain
+    m = ref_mcem.MCEM_M2(niter=niter, nsamples_E_step=nE, burnin_E_step=bE, nsamples_WF=nW, burnin_WF=bW, var_RW=0.01)
+    m.init_parameters(X=X, y=y, vae=vae, nmf_rank=K, eps=1e-8, device="cpu")
+    cost = m.run()
+    ref_mcem.torch = torch
+    s_hat = stft_oracle.istft(m.S_hat, fs=16000, wlen_sec=64e-3, win="hann", hop_percent=0.25, max_len=T)
+    ratios = np.array(energy_ratios(s_hat.astype(np.float64), sp, no))
+    draws = tape.draws
+    eps_ = np.stack([t.numpy() for k, t in draws[2:] if k == "randn"])
+    u_ = np.stack([t.numpy() for k, t in draws[2:] if k == "rand"])
+    sd = {"sd_" + k: v.numpy() for k, v in vae.state_dict().items()}
+    np.savez_compressed(os.path.join(OUT, "mcem_%s.npz" % tag), model="M2", y_kind="vad", L=L, K=K, niter=niter, chain=np.array(chain),
+                        var_RW=0.01, eps=1e-8, x=x, s=sp, n=no, X=X, y=y.numpy(), rand_W=draws[0][1].numpy(), rand_H=draws[1][1].numpy(),
+                        tape_eps=eps_, tape_u=u_, cost=cost, S_hat=m.S_hat, N_hat=m.N_hat, ratios=ratios, **sd)
+    print("golden %s: N=%d, VAD active %.2f, cost %s, SI-SDR/SIR/SAR %s (input SI-SDR %.2f dB)"
+          % (tag, N, float(y_np.mean()), np.round(cost, 4), np.round(ratios, 3), energy_ratios(x, sp, no)[0]))
+
+
 def golden_spp():
     """timo_mask_estimation (python/models/spp_estimation.py:198-218) of the reference on a synthetic mixture."""
     sys.path.insert(0, REF)
@@ -273,3 +324,4 @@ if __name__ == "__main__":
     golden_mcem("M2_vad", "M2", "vad", L=32, K=10, niter=2, chain=(2, 3, 2, 3))
     golden_nonmf()
     golden_spp()
+    golden_real()

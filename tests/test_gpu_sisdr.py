@@ -123,3 +123,39 @@ def test_enhance_many_equals_enhance():
             np.testing.assert_array_equal(s_hat[i, :T[i]], s_ref[i])
             ref = energy_ratios(s_ref[i].astype(np.float64), it["refs"][0][i], it["refs"][1][i])
             np.testing.assert_allclose(metrics[i], ref, rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "f16"])
+def test_real_wsj0_slice_matches_reference_golden(precision):
+    """Real speech + noise from the reference's own fixture, enhanced by the unmodified reference (tests/golden/
+    mcem_M2_vad_wsj0.npz): the CUDA path on the same tape with the same decisions gives the same cost and the same
+    SI-SDR / SI-SIR / SI-SAR (north star: within 0.05 dB)."""
+    from _util import load_golden, golden_state_dict, oracle_from_golden
+    from gvn import engine as E
+    from python.models.mcem import MCEM_M2
+    from python.models.models import DeepGenerativeModel
+    from python.processing.stft import istft
+    g = load_golden("M2_vad_wsj0")
+    o = oracle_from_golden(g)
+    o.trace = []
+    o.run()
+    forced = np.stack([t[1].numpy() for t in o.trace])
+    F, L = g["X"].shape[1], int(g["L"])
+    vae = DeepGenerativeModel([F, 1, L, [128, 128]], None)
+    vae.load_state_dict(golden_state_dict(g))
+    nE, bE, nW, bW = [int(v) for v in g["chain"]]
+    m = MCEM_M2(int(g["niter"]), nE, bE, nW, bW, float(g["var_RW"]))
+    m.precision = precision
+    m.replay = dict(rand_W=g["rand_W"], rand_H=g["rand_H"], eps=g["tape_eps"], u=g["tape_u"], forced=forced)
+    m.init_parameters(X=g["X"], y=torch.from_numpy(g["y"]).cuda(), vae=vae.eval(), nmf_rank=int(g["K"]), eps=float(g["eps"]), device="cuda:0")
+    cost = m.run()
+    np.testing.assert_allclose(cost, g["cost"], rtol=1e-4 if precision == "fp32" else 2e-3)
+    T = len(g["x"])
+    s_hat = istft(m.S_hat, max_len=T, **KW)
+    from python.metrics import energy_ratios
+    r = np.array(energy_ratios(s_hat.astype(np.float64), g["s"], g["n"]))
+    assert np.max(np.abs(r - g["ratios"])) < 0.05, (r, g["ratios"])
+    # the same three numbers from the device kernel (gvn_energy_ratios)
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).cuda().reshape(1, -1)
+    rd = E.energy_ratios(dev(s_hat), dev(g["s"]), dev(g["n"]), [T]).cpu().numpy()[0]
+    assert np.max(np.abs(rd - g["ratios"])) < 0.05, (rd, g["ratios"])
