@@ -191,6 +191,9 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        # host side of a rank = packing waveforms/labels into pinned memory: share the cores between the ranks instead of
+        # letting every process start one intra-op thread per core
+        torch.set_num_threads(max(1, (os.cpu_count() or 1) // world))
 
     cfg = McemConfig(model="M2", niter=args.niter, nmf_rank=args.rank_k, precision=args.precision,
                      mstep_variant=args.mstep_variant)
