@@ -21,7 +21,9 @@
 //     ring of [32 frequency rows][128 frames] boxes, produced by a dedicated warp;
 //   * the epilogue lives on the special-function pipe (exp per bin, log and reciprocal of Vx, 8 cycles
 //     per warp instruction and scheduler): bins are processed in pairs, log a + log b = log(ab) and
-//     x/a + y/b = (xb + ya)/(ab), one lg2 and one rcp per pair; tanh as tanh.approx.f16x2;
+//     x/a + y/b = (xb + ya)/(ab); the pair products are split into exponent and mantissa (integer sums / a running
+//     product < 2^8) and the quotients carried as one fraction, so a stage of 8 pairs needs ONE lg2 and ONE rcp;
+//     tanh as tanh.approx.f16x2;
 //   * the per-frame bias of the first layer (label projection + b1) sits in TMEM for the whole chain;
 //     the proposal noise and log u of step m+1 are drawn by the warps that idle while the owners
 //     accept/propose in step m and handed over through TMEM (L <= 16).
@@ -48,7 +50,7 @@ constexpr int NEW = NE / 32;            // epilogue warps
 constexpr int NTHREADS = 320;
 constexpr int STAGE_BYTES = SROWS * TM * 4;
 #ifndef GVN_TC_DEFAULT_VARIANT
-#define GVN_TC_DEFAULT_VARIANT 19
+#define GVN_TC_DEFAULT_VARIANT 22
 #endif
 
 // TMEM column map (512 columns allocated)
@@ -373,9 +375,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_estep_tc(const __grid_constant_
         // one stage = this thread's 16 bins of a 32-row ring box; the accumulator columns of stage s+1
         // are requested from TMEM before the math of stage s (two register sets, statically indexed)
         constexpr bool V_PF = (VAR & 1) != 0;             // prefetch the next stage's accumulator columns
-        constexpr bool V_PRE = false;
         constexpr bool V_PROBE = (VAR & 2) != 0;          // probe the next stage's ring barrier before this stage's math
-        constexpr bool V_PACK = false;                    // packed f32x2 arithmetic in the pair loop (measured slower, kept for reference)
         constexpr bool V_FRAC = (VAR & 4) != 0;           // one lg2 + one rcp per 8 pairs: exponent/mantissa split of the pair products
         auto stage = [&](uint32_t (&r)[16], uint32_t (&rn)[16], int s_) {
           const int f0 = c * 128 + s_ * SROWS + 16 * half;
@@ -396,37 +396,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_estep_tc(const __grid_constant_
           float* vo = STORE ? vs_out + tile_off(f0, n, F) : nullptr;              // column-tile order: bin stride = GVN_VS_TILE floats
           if (f0 + 16 <= F) {                              // full group: 8 pairs of bins
             float b3v[16];
-            uint32_t wv[16];
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) {
               const float4 t = *reinterpret_cast<const float4*>(sB3 + f0 + 4 * j4);
               b3v[4 * j4] = t.x; b3v[4 * j4 + 1] = t.y; b3v[4 * j4 + 2] = t.z; b3v[4 * j4 + 3] = t.w;
             }
-            if (ENERGY && V_PRE) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) wv[j] = xv[j * TM];
-              asm volatile("" ::: "memory");
-            }
             if (!V_PF) tmem_ld_wait();
-            if (V_PACK) {                                  // packed f32x2 arithmetic (FFMA2) where two bins run in lock step
-              float2 acc2 = make_float2(sl, sr);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float2 t = __ffma2_rn(make_float2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1])), make_float2(SC3, SC3),
-                                            make_float2(b3v[2 * j], b3v[2 * j + 1]));
-                const float v0 = ex2_approx(t.x), v1 = ex2_approx(t.y);
-                if (ENERGY) {
-                  const uint32_t w0 = V_PRE ? wv[2 * j] : xv[(2 * j) * TM], w1 = V_PRE ? wv[2 * j + 1] : xv[(2 * j + 1) * TM];
-                  const float2 ab = __ffma2_rn(make_float2(g, g), make_float2(v0, v1),
-                                               make_float2(__uint_as_float(w0 << 16), __uint_as_float(w1 << 16)));
-                  const float pr = ab.x * ab.y;
-                  const float qn = fmaf(__uint_as_float(w0), ab.y, __uint_as_float(w1) * ab.x);
-                  acc2 = __ffma2_rn(make_float2(1.0f, qn), make_float2(lg2_approx(pr), rcp_approx(pr)), acc2);
-                }
-                if (STORE && valid) { st_stream(vo + (2 * j) * GVN_VS_TILE, v0); st_stream(vo + (2 * j + 1) * GVN_VS_TILE, v1); }
-              }
-              sl = acc2.x; sr = acc2.y;
-            } else if (V_FRAC && ENERGY) {
+            if (V_FRAC && ENERGY) {
               // sum_j log(pr_j) = ln2 * (sum_j e_j + lg2(prod_j m_j)) and sum_j qn_j/pr_j = N/P with pr_j = m_j * 2^e_j,
               // m_j in [1,2): the exponents are summed as integers, the mantissas multiplied (P < 2^8), the quotients
               // (scaled by 2^-e_j, exact) carried as one fraction N/P -- 2 special-function operations per 8 pairs
@@ -459,7 +435,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_estep_tc(const __grid_constant_
               const float v0 = ex2_approx(t0);
               const float v1 = ex2_approx(t1);
               if (ENERGY) {
-                const uint32_t w0 = V_PRE ? wv[2 * j] : xv[(2 * j) * TM], w1 = V_PRE ? wv[2 * j + 1] : xv[(2 * j + 1) * TM];
+                const uint32_t w0 = xv[(2 * j) * TM], w1 = xv[(2 * j + 1) * TM];
                 const float a = fmaf(g, v0, __uint_as_float(w0 << 16)), b = fmaf(g, v1, __uint_as_float(w1 << 16));
                 const float pr = a * b;
                 sl += lg2_approx(pr);
@@ -690,7 +666,7 @@ int32_t launch_estep_tc(const gvn_batch* b, const void* packed, int burnin, int 
     switch (var) {
       case 0: return launch_tc<16, false, 0>(mx, a, grid, st);
       case 3: return launch_tc<16, false, 3>(mx, a, grid, st);
-      case 11: return launch_tc<16, false, 11>(mx, a, grid, st);
+      case 19: return launch_tc<16, false, 19>(mx, a, grid, st);
       case 23: return launch_tc<16, false, 23>(mx, a, grid, st);
       default: return launch_tc<16, false, GVN_TC_DEFAULT_VARIANT>(mx, a, grid, st);
     }
