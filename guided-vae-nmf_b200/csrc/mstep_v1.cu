@@ -387,10 +387,13 @@ __host__ __device__ inline size_t cols_smem_floats(int F, int KS, int K, int R, 
 
 __device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, %0;" ::"n"(CCT) : "memory"); }
 
-template <int KMAX, int RT>
+// FT > 0: the number of frequency bins is a compile-time constant (513 in every evaluate script), so the slot offsets
+// r * F * 8 of the inner loops become immediates instead of one integer multiply-add per slot and row
+template <int KMAX, int RT, int FT = 0>
 __global__ void __launch_bounds__(CTT, 1) k_cols_v1(ColsArgs p) {
   extern __shared__ __align__(128) float sm[];
-  const int F = p.F, K = p.K, KS = p.KS, NP = p.NP;
+  const int F = FT > 0 ? FT : p.F, K = p.K, NP = p.NP;
+  constexpr int KS = (KMAX % 16 == 0) ? KMAX + 4 : KMAX;     // dictionary row stride in shared memory (= ks_of(K), the launcher sizes with it)
   const int R = RT > 0 ? RT : p.R;
   const int MR = K + 1 + R;
   const int PS = F * NB;                                    // plane stride (floats); a plane is one bulk-contiguous block
@@ -455,6 +458,7 @@ __global__ void __launch_bounds__(CTT, 1) k_cols_v1(ColsArgs p) {
 
   // ================= compute warps =================
   const int n = tid & (NB - 1), fl = tid >> 3;              // column of the tile, frequency lane
+  const int my_ni = (F - fl + CFL - 1) / CFL;               // rows of this thread: fl, fl + CFL, ... (no bound check inside the loops)
   int cur_b = -1, cur_fo = -1;
   uint32_t par = 0;                                         // phase parity of the barriers for this tile
   for (int t = t_hi - 1; t >= t_lo; --t, par ^= 1) {
@@ -509,11 +513,11 @@ __global__ void __launch_bounds__(CTT, 1) k_cols_v1(ColsArgs p) {
     for (int k = 0; k < KMAX; ++k) num[k] = den[k] = 0.f;
     for (int j = 0; j < NCH; ++j) {
       mbar_wait(full + j, par);
-      const int i0 = cb[j], i1 = cb[j + 1];
+      const int i0 = cb[j], i1 = min(cb[j + 1], my_ni);
       const float* vs = data + (size_t)(i0 * CFL + fl) * NB + n;
       const float* wrow = W_s + (i0 * CFL + fl) * KS;
       for (int i = i0; i < i1; ++i, vs += CFL * NB, wrow += CFL * KS) {
-        if (i * CFL + fl < F) {
+        {
           float w[KMAX];
 #pragma unroll
           for (int k4 = 0; k4 < KMAX; k4 += 4) {
@@ -597,8 +601,8 @@ __global__ void __launch_bounds__(CTT, 1) k_cols_v1(ColsArgs p) {
       const size_t vstep = (size_t)CFL * NP;
       float* vbo = p.Vb + (size_t)fl * NP + (size_t)t * NB + n;
       uint32_t* xvo = p.XV != nullptr ? p.XV + (size_t)fl * NP + (size_t)t * NB + n : nullptr;
-      for (int i = 0; i < NI; ++i, vs += CFL * NB, wrow += CFL * KS, vbo += vstep) {
-        if (i * CFL + fl < F) {
+      for (int i = 0; i < my_ni; ++i, vs += CFL * NB, wrow += CFL * KS, vbo += vstep, xvo += vstep) {
+        {
           f2 vbp = F2(0.f, 0.f);
 #pragma unroll
           for (int k4 = 0; k4 < KMAX; k4 += 4) {
@@ -606,7 +610,7 @@ __global__ void __launch_bounds__(CTT, 1) k_cols_v1(ColsArgs p) {
             vbp = fma2(F2(t4.x, t4.y), F2(hn[k4], hn[k4 + 1]), fma2(F2(t4.z, t4.w), F2(hn[k4 + 2], hn[k4 + 3]), vbp));
           }
           const float vb = vbp.x + vbp.y;
-          if (valid) { *vbo = vb; if (xvo != nullptr) xvo[(size_t)i * vstep] = pack_xv_word(vs[R * PS], vb); }
+          if (valid) { *vbo = vb; if (p.XV != nullptr) *xvo = pack_xv_word(vs[R * PS], vb); }
           float t1 = 0.f, t2 = 0.f;
           f2 t1v = F2(0.f, 0.f), t2v = F2(0.f, 0.f);
           const f2 g2 = F2(gg, gg), vb2 = F2(vb, vb);
@@ -665,11 +669,11 @@ __global__ void __launch_bounds__(CTT, 1) k_cols_v1(ColsArgs p) {
     // ---------------- pass C: cost with the new g (mcem.py:151-152, :68-70); chunks are released behind it
     float cl = 0.f, cr = 0.f;
     for (int j = 0; j < NCH; ++j) {
-      const int i0 = cb[j], i1 = cb[j + 1];
+      const int i0 = cb[j], i1 = min(cb[j + 1], my_ni);
       const float* vs = data + (size_t)(i0 * CFL + fl) * NB + n;
       const float* wrow = W_s + (i0 * CFL + fl) * KS;
       for (int i = i0; i < i1; ++i, vs += CFL * NB, wrow += CFL * KS) {
-        if (i * CFL + fl < F) {
+        {
           f2 vbp = F2(0.f, 0.f);
 #pragma unroll
           for (int k4 = 0; k4 < KMAX; k4 += 4) {
@@ -929,16 +933,16 @@ int32_t launch_cols_gen(const GenArgs& a, size_t smem, int grid, cudaStream_t st
   return check_launch("k_cols_gen");
 }
 
-template <int KMAX, int RT>
+template <int KMAX, int RT, int FT = 0>
 int32_t launch_cols(const ColsArgs& a, size_t smem, int grid, cudaStream_t st) {
   static size_t smem_tab[GVN_MAX_DEVICES] = {0};
   size_t& smem_set = *per_device_slot(smem_tab);
   if (smem_set != smem) {
-    cudaError_t e = cudaFuncSetAttribute(k_cols_v1<KMAX, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k_cols_v1<KMAX, RT, FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(GVN_E_CUDA, "k_cols_v1 smem attr (%zu B): %s", smem, cudaGetErrorString(e));
     smem_set = smem;
   }
-  k_cols_v1<KMAX, RT><<<grid, CTT, smem, st>>>(a);
+  k_cols_v1<KMAX, RT, FT><<<grid, CTT, smem, st>>>(a);
   return check_launch("k_cols_v1");
 }
 
@@ -988,7 +992,8 @@ int32_t launch_v1_k(const gvn_batch* b, int R, const ColsArgs& a, size_t smem, i
   float* Wpart = const_cast<float*>(a.Mt) + (size_t)(b->K + 1 + b->R_cap) * b->NP;     // behind the column data (mstep_v1_workspace_bytes)
   int32_t rc = R == 10 ? launch_w<KMAX, 10>(b, R, a.Mt, Wpart, st) : launch_w<KMAX, 0>(b, R, a.Mt, Wpart, st);
   if (rc) return rc;
-  return R == 10 ? launch_cols<KMAX, 10>(a, smem, grid, st) : launch_cols<KMAX, 0>(a, smem, grid, st);
+  if (R == 10) return b->F == 513 ? launch_cols<KMAX, 10, 513>(a, smem, grid, st) : launch_cols<KMAX, 10>(a, smem, grid, st);
+  return launch_cols<KMAX, 0>(a, smem, grid, st);
 }
 
 }  // namespace
