@@ -461,9 +461,14 @@ __global__ void __launch_bounds__(CTT, 1) k_cols_v1(ColsArgs p) {
   const int my_ni = (F - fl + CFL - 1) / CFL;               // rows of this thread: fl, fl + CFL, ... (no bound check inside the loops)
   int cur_b = -1, cur_fo = -1;
   uint32_t par = 0;                                         // phase parity of the barriers for this tile
+  // utterance of the tile and validity of this thread's frame, fetched one tile ahead (an L2 round trip otherwise sits at
+  // the head of every tile)
+  int b_nxt = p.frame_utt[(size_t)(t_hi - 1) * NB], v_nxt = p.frame_utt[(size_t)(t_hi - 1) * NB + n];
   for (int t = t_hi - 1; t >= t_lo; --t, par ^= 1) {
+    const int b = b_nxt;                                    // tiles never straddle utterances (32-frame alignment)
+    const bool valid = v_nxt >= 0;
+    if (t > t_lo) { b_nxt = p.frame_utt[(size_t)(t - 1) * NB]; v_nxt = p.frame_utt[(size_t)(t - 1) * NB + n]; }
     mbar_wait(mfull, par);
-    const int b = p.frame_utt[(size_t)t * NB];              // tiles never straddle utterances (32-frame alignment)
     if (b < 0) {                                            // tile entirely in padding: drain its copies, move on
       for (int j = 0; j < NCH; ++j) mbar_wait(full + j, par);
       if (tid == 0) p.cost_part[t] = 0.f;
@@ -471,7 +476,6 @@ __global__ void __launch_bounds__(CTT, 1) k_cols_v1(ColsArgs p) {
       if (lane == 0) { mbar_arrive(mempty); for (int j = 0; j < NCH; ++j) mbar_arrive(empty + j); }
       continue;
     }
-    const bool valid = p.frame_utt[(size_t)t * NB + n] >= 0;
     const float gg = meta[K * NB + n];
     float hk[KMAX];
 #pragma unroll
@@ -573,16 +577,12 @@ __global__ void __launch_bounds__(CTT, 1) k_cols_v1(ColsArgs p) {
       }
     }
     bar_compute();
-    if (tid < 2 * KMAX * NB) {
-      float s = 0.f;
-#pragma unroll
-      for (int w8 = 0; w8 < CW; ++w8) s += red[w8 * 2 * KMAX * NB + tid];
-      red2[tid] = s;
-    }
-    bar_compute();
-    if (tid < KMAX * NB) {
+    if (tid < KMAX * NB) {                                  // thread (k, n): both sums over the warps, then the update (one barrier less)
       const int k = tid >> 3;
-      Hn_s[tid] = (k < K) ? meta[tid] * sqrtf(red2[tid] / red2[KMAX * NB + tid]) : 0.f;
+      float nu = 0.f, de = 0.f;
+#pragma unroll
+      for (int w8 = 0; w8 < CW; ++w8) { nu += red[w8 * 2 * KMAX * NB + tid]; de += red[w8 * 2 * KMAX * NB + KMAX * NB + tid]; }
+      Hn_s[tid] = (k < K) ? meta[tid] * sqrtf(nu / de) : 0.f;
     }
     bar_compute();
     float hn[KMAX];
