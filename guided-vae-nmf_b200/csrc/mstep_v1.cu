@@ -162,7 +162,8 @@ constexpr int WS = 4;                 // ring stages at most (two CTAs per SM: 8
 // floats of one ring stage: (R+1) planes of [WROWS][NB] + column data (H rows, g, multiplicities)
 __host__ __device__ inline int w_stage_floats(int K, int R) { return ((R + 1) * WROWS * NB + (K + 1 + R) * NB + 31) / 32 * 32; }
 
-template <int KMAX, int RT>
+// KX > 0: the rank is exactly KX (10 in every evaluate script): no guards, no padded columns in the rank-K loops
+template <int KMAX, int RT, int KX = 0>
 __global__ void __launch_bounds__(WT, (KMAX > 16 ? 1 : 2)) k_w_v2(int F, int K, int NP, int R_rt, int ws, const int32_t* __restrict__ frame_off,
                                                 const int32_t* __restrict__ n_frames, const float* __restrict__ X2t,
                                                 const float* __restrict__ Vs, const float* __restrict__ Mt,
@@ -293,9 +294,10 @@ __global__ void __launch_bounds__(WT, (KMAX > 16 ? 1 : 2)) k_w_v2(int F, int K, 
     }
     return;
   }
-  float w[KMAX], num[KMAX], den[KMAX];
+  constexpr int KE = KX > 0 ? KX : KMAX;                    // columns the rank-K loops run over
+  float w[KE], num[KE], den[KE];
 #pragma unroll
-  for (int k = 0; k < KMAX; ++k) { w[k] = (k < K && rowok) ? W[((size_t)b * F + f) * K + k] : 0.f; num[k] = den[k] = 0.f; }
+  for (int k = 0; k < KE; ++k) { w[k] = (k < K && rowok) ? W[((size_t)b * F + f) * K + k] : 0.f; num[k] = den[k] = 0.f; }
 
   for (int ti = 0; ti < ntile; ++ti) {
     const int s = ti % ws;
@@ -306,7 +308,7 @@ __global__ void __launch_bounds__(WT, (KMAX > 16 ? 1 : 2)) k_w_v2(int F, int K, 
       const float* mt = st + MO + n;                        // column data of frame n
       float vb = 0.f;
 #pragma unroll
-      for (int k = 0; k < KMAX; ++k) if (k < K) vb = fmaf(w[k], mt[k * NB], vb);
+      for (int k = 0; k < KE; ++k) if (KX > 0 || k < K) vb = fmaf(w[k], mt[k * NB], vb);
       const float gg = mt[K * NB];
       const float* wt = mt + (K + 1) * NB;
       float s1 = 0.f, s2 = 0.f;
@@ -322,14 +324,14 @@ __global__ void __launch_bounds__(WT, (KMAX > 16 ? 1 : 2)) k_w_v2(int F, int K, 
       float a = vs[R * PSt] * s2;
       if ((tb + ti) * NB + n >= N) { a = 0.f; s1 = 0.f; }   // padding frames of the last tile contribute nothing
 #pragma unroll
-      for (int k = 0; k < KMAX; ++k) if (k < K) { const float h = mt[k * NB]; num[k] = fmaf(a, h, num[k]); den[k] = fmaf(s1, h, den[k]); }
+      for (int k = 0; k < KE; ++k) if (KX > 0 || k < K) { const float h = mt[k * NB]; num[k] = fmaf(a, h, num[k]); den[k] = fmaf(s1, h, den[k]); }
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(empty + s);                  // this warp is done with stage s
   }
   // reduce over the 8 columns of the tile (adjacent lanes), lane n == 0 writes the row
 #pragma unroll
-  for (int k = 0; k < KMAX; ++k) {
+  for (int k = 0; k < KE; ++k) {
 #pragma unroll
     for (int o = 4; o > 0; o >>= 1) {
       num[k] += __shfl_xor_sync(0xffffffffu, num[k], o);
@@ -339,12 +341,12 @@ __global__ void __launch_bounds__(WT, (KMAX > 16 ? 1 : 2)) k_w_v2(int F, int K, 
   if (n == 0 && rowok) {
     if (nsplit == 1) {
 #pragma unroll
-      for (int k = 0; k < KMAX; ++k)
+      for (int k = 0; k < KE; ++k)
         if (k < K) Wun[((size_t)b * F + f) * K + k] = w[k] * sqrtf(num[k] / den[k]);
     } else {
       float* dst = Wpart + ((((size_t)b * nsplit + blockIdx.z) * F + f) * K) * 2;
 #pragma unroll
-      for (int k = 0; k < KMAX; ++k)
+      for (int k = 0; k < KE; ++k)
         if (k < K) { dst[2 * k] = num[k]; dst[2 * k + 1] = den[k]; }
     }
   }
@@ -959,7 +961,7 @@ inline int w_nsplit(const gvn_batch* b) {
   return ns < 1 ? 1 : ns;
 }
 
-template <int KMAX, int RT>
+template <int KMAX, int RT, int KX = 0>
 int32_t launch_w(const gvn_batch* b, int R, const float* Mt, float* Wpart, cudaStream_t st) {
   const size_t stage = (size_t)w_stage_floats(b->K, R) * 4;
   const size_t budget = (KMAX > 16 || 2 * stage > 100 * 1024 ? 200 : 100) * 1024;    // one or two CTAs per SM
@@ -970,13 +972,13 @@ int32_t launch_w(const gvn_batch* b, int R, const float* Mt, float* Wpart, cudaS
   static size_t smem_tab[GVN_MAX_DEVICES] = {0};
   size_t& smem_set = *per_device_slot(smem_tab);
   if (smem_set != smem) {
-    cudaError_t e = cudaFuncSetAttribute(k_w_v2<KMAX, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k_w_v2<KMAX, RT, KX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(GVN_E_CUDA, "k_w_v2 smem attr (%zu B): %s", smem, cudaGetErrorString(e));
     smem_set = smem;
   }
   const int nsplit = w_nsplit(b);
   dim3 gw((b->F + WROWS - 1) / WROWS, b->B, nsplit);
-  k_w_v2<KMAX, RT><<<gw, WT, smem, st>>>(b->F, b->K, b->NP, R, ws, b->frame_off, b->n_frames, b->X2t, b->Vs, Mt, b->W, b->Wun, Wpart);
+  k_w_v2<KMAX, RT, KX><<<gw, WT, smem, st>>>(b->F, b->K, b->NP, R, ws, b->frame_off, b->n_frames, b->X2t, b->Vs, Mt, b->W, b->Wun, Wpart);
   int32_t rc = check_launch("k_w_v2");
   if (rc || nsplit == 1) return rc;
   const size_t total = (size_t)b->B * b->F * b->K;
@@ -990,7 +992,9 @@ inline int ks_of(int K) { int ks = kmax_of(K); return (ks % 16 == 0) ? ks + 4 : 
 template <int KMAX>
 int32_t launch_v1_k(const gvn_batch* b, int R, const ColsArgs& a, size_t smem, int grid, cudaStream_t st) {
   float* Wpart = const_cast<float*>(a.Mt) + (size_t)(b->K + 1 + b->R_cap) * b->NP;     // behind the column data (mstep_v1_workspace_bytes)
-  int32_t rc = R == 10 ? launch_w<KMAX, 10>(b, R, a.Mt, Wpart, st) : launch_w<KMAX, 0>(b, R, a.Mt, Wpart, st);
+  int32_t rc;
+  if (R == 10) rc = (KMAX == 12 && b->K == 10) ? launch_w<KMAX, 10, (KMAX == 12 ? 10 : 0)>(b, R, a.Mt, Wpart, st) : launch_w<KMAX, 10>(b, R, a.Mt, Wpart, st);
+  else rc = launch_w<KMAX, 0>(b, R, a.Mt, Wpart, st);
   if (rc) return rc;
   if (R == 10) return b->F == 513 ? launch_cols<KMAX, 10, 513>(a, smem, grid, st) : launch_cols<KMAX, 10>(a, smem, grid, st);
   return launch_cols<KMAX, 0>(a, smem, grid, st);
