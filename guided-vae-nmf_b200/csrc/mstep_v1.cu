@@ -135,15 +135,17 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 // ------------------------------------------------------------------ column data in tile order
 // Mt[t][K+1+R][8]: rows 0..K-1 = H, row K = g, rows K+1.. = slot multiplicities of the 8 frames of
 // column tile t -- one contiguous block per tile, so a stage needs ONE copy for all of it.
+// Thread = column; a CTA covers 256 consecutive columns (32 tiles) and walks the rows: coalesced reads of one row of
+// H / g / Vs_w, 32-byte segments on the write side, no integer division.
 __global__ void __launch_bounds__(256) k_tile_meta(int K, int R, int NP, const float* __restrict__ H, const float* __restrict__ g,
                                                    const float* __restrict__ Vs_w, float* __restrict__ Mt) {
   const int MR = K + 1 + R;
-  const size_t total = (size_t)MR * NP;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int n8 = (int)(i & 7), m = (int)((i >> 3) % MR);
-    const size_t t = (i >> 3) / MR, col = t * NB + n8;
-    Mt[i] = m < K ? H[(size_t)m * NP + col] : (m == K ? g[col] : Vs_w[(size_t)(m - K - 1) * NP + col]);
-  }
+  const int col = blockIdx.x * 256 + threadIdx.x;
+  if (col >= NP) return;
+  float* dst = Mt + (size_t)(col / NB) * MR * NB + (col & (NB - 1));
+  for (int m = 0; m < K; ++m) dst[m * NB] = H[(size_t)m * NP + col];
+  dst[K * NB] = g[col];
+  for (int r = 0; r < R; ++r) dst[(K + 1 + r) * NB] = Vs_w[(size_t)r * NP + col];
 }
 
 // ------------------------------------------------------------------ W update (mcem.py:105-110)
@@ -1027,7 +1029,7 @@ size_t mstep_v1_workspace_bytes(const gvn_batch* b) {
 }
 
 int32_t launch_mstep_v1(const gvn_batch* b, int R, float* cost_part, float* Mt, cudaStream_t st) {
-  k_tile_meta<<<148, 256, 0, st>>>(b->K, R, b->NP, b->H, b->g, b->Vs_w, Mt);
+  k_tile_meta<<<(b->NP + 255) / 256, 256, 0, st>>>(b->K, R, b->NP, b->H, b->g, b->Vs_w, Mt);
   int32_t rc = check_launch("k_tile_meta");
   if (rc) return rc;
   static int sms = 0;
