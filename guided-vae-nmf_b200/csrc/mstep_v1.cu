@@ -133,19 +133,33 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
 // ------------------------------------------------------------------ column data in tile order
-// Mt[t][K+1+R][8]: rows 0..K-1 = H, row K = g, rows K+1.. = slot multiplicities of the 8 frames of
-// column tile t -- one contiguous block per tile, so a stage needs ONE copy for all of it.
-// Thread = column; a CTA covers 256 consecutive columns (32 tiles) and walks the rows: coalesced reads of one row of
-// H / g / Vs_w, 32-byte segments on the write side, no integer division.
+// Mt[t][n][MS]: one record of MS floats per frame n of column tile t -- H[0..K), g, the R slot multiplicities, padding --
+// so a stage needs ONE bulk copy for the column data of a tile and a thread reads its frame's record with 16-byte loads.
+// MS = 4 * (odd number): the records of the 8 frames of a tile start in different bank groups.
+__host__ __device__ inline int meta_stride(int K, int R) {
+  int m = (K + 1 + R + 3) / 4;
+  if ((m & 1) == 0) ++m;
+  return 4 * m;
+}
+
 __global__ void __launch_bounds__(256) k_tile_meta(int K, int R, int NP, const float* __restrict__ H, const float* __restrict__ g,
                                                    const float* __restrict__ Vs_w, float* __restrict__ Mt) {
-  const int MR = K + 1 + R;
-  const int col = blockIdx.x * 256 + threadIdx.x;
-  if (col >= NP) return;
-  float* dst = Mt + (size_t)(col / NB) * MR * NB + (col & (NB - 1));
-  for (int m = 0; m < K; ++m) dst[m * NB] = H[(size_t)m * NP + col];
-  dst[K * NB] = g[col];
-  for (int r = 0; r < R; ++r) dst[(K + 1 + r) * NB] = Vs_w[(size_t)r * NP + col];
+  __shared__ float rec[256 * 29 + 32];                        // records of 256 columns, staged so that the writes are coalesced
+  const int MS = meta_stride(K, R), MR = K + 1 + R;
+  const int c0 = blockIdx.x * 256, col = c0 + threadIdx.x;
+  const bool staged = MS <= 29;
+  if (col < NP) {
+    float* dst = staged ? rec + threadIdx.x * MS : Mt + (size_t)col * MS;
+    for (int m = 0; m < K; ++m) dst[m] = H[(size_t)m * NP + col];
+    dst[K] = g[col];
+    for (int r = 0; r < R; ++r) dst[K + 1 + r] = Vs_w[(size_t)r * NP + col];
+    for (int m = MR; m < MS; ++m) dst[m] = 0.f;
+  }
+  if (staged) {
+    __syncthreads();
+    const int ncol = min(256, NP - c0);
+    for (int i = threadIdx.x; i < ncol * MS; i += 256) Mt[(size_t)c0 * MS + i] = rec[i];
+  }
 }
 
 // ------------------------------------------------------------------ W update (mcem.py:105-110)
@@ -162,7 +176,7 @@ constexpr int WT = WCT + 32;          // + producer warp
 constexpr int WS = 4;                 // ring stages at most (two CTAs per SM: 8 stages of ~23 KB in flight at R = 10)
 
 // floats of one ring stage: (R+1) planes of [WROWS][NB] + column data (H rows, g, multiplicities)
-__host__ __device__ inline int w_stage_floats(int K, int R) { return ((R + 1) * WROWS * NB + (K + 1 + R) * NB + 31) / 32 * 32; }
+__host__ __device__ inline int w_stage_floats(int K, int R) { return ((R + 1) * WROWS * NB + meta_stride(K, R) * NB + 31) / 32 * 32; }
 
 // KX > 0: the rank is exactly KX (10 in every evaluate script): no guards, no padded columns in the rank-K loops
 template <int KMAX, int RT, int KX = 0>
@@ -185,7 +199,7 @@ __global__ void __launch_bounds__(WT, (KMAX > 16 ? 1 : 2)) k_w_v2(int F, int K, 
   const int ntile = te - tb, t0 = n_begin / NB + tb, T8 = NP / NB;
   constexpr int PSt = WROWS * NB;                           // plane stride inside a stage (floats)
   const int MO = (R + 1) * PSt;                             // offset of the column data inside a stage
-  const int MR = K + 1 + R;
+  const int MS = meta_stride(K, R);                         // floats per frame record of the column data
   const int SSt = w_stage_floats(K, R);
 
   if (tid == 0) {
@@ -201,12 +215,12 @@ __global__ void __launch_bounds__(WT, (KMAX > 16 ? 1 : 2)) k_w_v2(int F, int K, 
       const int s = ti % ws;
       if (ti >= ws) mbar_wait(empty + s, ((ti / ws) - 1) & 1);
       float* dst = smw + (size_t)s * SSt;
-      if (lane == 0) mbar_expect_tx(full + s, blk * (R + 1) + (uint32_t)MR * NB * 4);
+      if (lane == 0) mbar_expect_tx(full + s, blk * (R + 1) + (uint32_t)MS * NB * 4);
       __syncwarp();
       for (int c = lane; c <= R + 1; c += 32) {
         if (c < R) bulk_g2s(dst + c * PSt, Vs + (((size_t)c * T8 + t0 + ti) * F + f0) * NB, blk, full + s);
         else if (c == R) bulk_g2s(dst + R * PSt, X2t + ((size_t)(t0 + ti) * F + f0) * NB, blk, full + s);
-        else bulk_g2s(dst + MO, Mt + (size_t)(t0 + ti) * MR * NB, (uint32_t)MR * NB * 4, full + s);
+        else bulk_g2s(dst + MO, Mt + (size_t)(t0 + ti) * MS * NB, (uint32_t)MS * NB * 4, full + s);
       }
     }
     return;
@@ -236,19 +250,19 @@ __global__ void __launch_bounds__(WT, (KMAX > 16 ? 1 : 2)) k_w_v2(int F, int K, 
       float a = 0.f, s1 = 0.f;
       if (rowok) {
         const float* vs = st + rl * NB + n;
-        const float* mt = mt0 + n;
+        const float* mt = mt0 + n * MS;                       // record of frame n
         float vb0 = 0.f, vb1 = 0.f;
 #pragma unroll
-        for (int k = 0; k < KMAX; k += 2) {                   // rows beyond K of the column data are not H
-          if (k < K) vb0 = fmaf(w[k], mt[k * NB], vb0);
-          if (k + 1 < K) vb1 = fmaf(w[k + 1], mt[(k + 1) * NB], vb1);
+        for (int k = 0; k < KMAX; k += 2) {                   // entries beyond K of the record are not H
+          if (k < K) vb0 = fmaf(w[k], mt[k], vb0);
+          if (k + 1 < K) vb1 = fmaf(w[k + 1], mt[k + 1], vb1);
         }
-        const float vb = vb0 + vb1, gg = mt[K * NB];
-        const float* wt = mt + (K + 1) * NB;
+        const float vb = vb0 + vb1, gg = mt[K];
+        const float* wt = mt + K + 1;
         float s2 = 0.f;
         int r = 0;
-        for (; r + 1 < R; r += 2) pair_acc(gg, vb, vs[r * PSt], vs[(r + 1) * PSt], wt[r * NB], wt[(r + 1) * NB], s1, s2);
-        if (r < R) single_acc(gg, vb, vs[r * PSt], wt[r * NB], s1, s2);
+        for (; r + 1 < R; r += 2) pair_acc(gg, vb, vs[r * PSt], vs[(r + 1) * PSt], wt[r], wt[r + 1], s1, s2);
+        if (r < R) single_acc(gg, vb, vs[r * PSt], wt[r], s1, s2);
         a = vs[R * PSt] * s2;
         if ((tb + ti) * NB + n >= N) { a = 0.f; s1 = 0.f; }
       }
@@ -263,18 +277,15 @@ __global__ void __launch_bounds__(WT, (KMAX > 16 ? 1 : 2)) k_w_v2(int F, int K, 
         av[j4] = t0_.x; av[j4 + 1] = t0_.y; av[j4 + 2] = t0_.z; av[j4 + 3] = t0_.w;
         sv[j4] = t1_.x; sv[j4 + 1] = t1_.y; sv[j4 + 2] = t1_.z; sv[j4 + 3] = t1_.w;
       }
+      static_assert(KG == 4, "phase 2 reads its dictionary columns as one float4 per frame");
 #pragma unroll
-      for (int i = 0; i < KG; ++i) {
-        const int k = kg * KG + i;
-        if (k < K) {
-          const float* hp = mt0 + k * NB;                   // H[k][0..7] of the stage
-#pragma unroll
-          for (int j4 = 0; j4 < NB; j4 += 4) {
-            const float4 h = *reinterpret_cast<const float4*>(hp + j4);
-            num[i] = fmaf(av[j4], h.x, fmaf(av[j4 + 1], h.y, fmaf(av[j4 + 2], h.z, fmaf(av[j4 + 3], h.w, num[i]))));
-            den[i] = fmaf(sv[j4], h.x, fmaf(sv[j4 + 1], h.y, fmaf(sv[j4 + 2], h.z, fmaf(sv[j4 + 3], h.w, den[i]))));
-          }
-        }
+      if (kg * KG < K)                                      // groups entirely beyond the rank have nothing to do (and would read past the record)
+      for (int j = 0; j < NB; ++j) {                        // H[4 kg .. 4 kg + 3] of frame j (entries beyond K are finite and never written out)
+        const float4 h = *reinterpret_cast<const float4*>(mt0 + j * MS + kg * KG);
+        num[0] = fmaf(av[j], h.x, num[0]); den[0] = fmaf(sv[j], h.x, den[0]);
+        num[1] = fmaf(av[j], h.y, num[1]); den[1] = fmaf(sv[j], h.y, den[1]);
+        num[2] = fmaf(av[j], h.z, num[2]); den[2] = fmaf(sv[j], h.z, den[2]);
+        num[3] = fmaf(av[j], h.w, num[3]); den[3] = fmaf(sv[j], h.w, den[3]);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(empty + s);                // this warp is done with stage s
@@ -307,26 +318,37 @@ __global__ void __launch_bounds__(WT, (KMAX > 16 ? 1 : 2)) k_w_v2(int F, int K, 
     if (rowok) {
       const float* st = smw + (size_t)s * SSt;
       const float* vs = st + rl * NB + n;
-      const float* mt = st + MO + n;                        // column data of frame n
+      const float* mt = st + MO + n * MS;                   // record of frame n: H | g | multiplicities
+      constexpr bool VEC = KX > 0 && RT > 0;                // all offsets known: the record is read with 16-byte loads
+      constexpr int NV = VEC ? (KX + 1 + RT + 3) / 4 * 4 : 4;
+      float md[NV];
+      if (VEC) {
+#pragma unroll
+        for (int q = 0; q < NV; q += 4) {
+          const float4 t4 = *reinterpret_cast<const float4*>(mt + q);
+          md[q] = t4.x; md[q + 1] = t4.y; md[q + 2] = t4.z; md[q + 3] = t4.w;
+        }
+      }
+      auto hval = [&](int k) -> float { return VEC ? md[VEC ? k : 0] : mt[k]; };
+      auto wval = [&](int r) -> float { return VEC ? md[VEC ? KX + 1 + r : 0] : mt[K + 1 + r]; };
       float vb = 0.f;
 #pragma unroll
-      for (int k = 0; k < KE; ++k) if (KX > 0 || k < K) vb = fmaf(w[k], mt[k * NB], vb);
-      const float gg = mt[K * NB];
-      const float* wt = mt + (K + 1) * NB;
+      for (int k = 0; k < KE; ++k) if (KX > 0 || k < K) vb = fmaf(w[k], hval(k), vb);
+      const float gg = VEC ? md[VEC ? KX : 0] : mt[K];
       float s1 = 0.f, s2 = 0.f;
       if (RT > 0) {
 #pragma unroll
-        for (int r = 0; r + 1 < RT; r += 2) pair_acc(gg, vb, vs[r * PSt], vs[(r + 1) * PSt], wt[r * NB], wt[(r + 1) * NB], s1, s2);
-        if (RT & 1) single_acc(gg, vb, vs[(RT - 1) * PSt], wt[(RT - 1) * NB], s1, s2);
+        for (int r = 0; r + 1 < RT; r += 2) pair_acc(gg, vb, vs[r * PSt], vs[(r + 1) * PSt], wval(r), wval(r + 1), s1, s2);
+        if (RT & 1) single_acc(gg, vb, vs[(RT - 1) * PSt], wval(RT - 1), s1, s2);
       } else {
         int r = 0;
-        for (; r + 1 < R; r += 2) pair_acc(gg, vb, vs[r * PSt], vs[(r + 1) * PSt], wt[r * NB], wt[(r + 1) * NB], s1, s2);
-        if (r < R) single_acc(gg, vb, vs[r * PSt], wt[r * NB], s1, s2);
+        for (; r + 1 < R; r += 2) pair_acc(gg, vb, vs[r * PSt], vs[(r + 1) * PSt], wval(r), wval(r + 1), s1, s2);
+        if (r < R) single_acc(gg, vb, vs[r * PSt], wval(r), s1, s2);
       }
       float a = vs[R * PSt] * s2;
       if ((tb + ti) * NB + n >= N) { a = 0.f; s1 = 0.f; }   // padding frames of the last tile contribute nothing
 #pragma unroll
-      for (int k = 0; k < KE; ++k) if (KX > 0 || k < K) { const float h = mt[k * NB]; num[k] = fmaf(a, h, num[k]); den[k] = fmaf(s1, h, den[k]); }
+      for (int k = 0; k < KE; ++k) if (KX > 0 || k < K) { const float h = hval(k); num[k] = fmaf(a, h, num[k]); den[k] = fmaf(s1, h, den[k]); }
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(empty + s);                  // this warp is done with stage s
@@ -383,10 +405,10 @@ constexpr int CW = CCT / 32;          // compute warps
 constexpr int CTT = CCT + 32;         // + producer warp
 
 // shared memory (floats): data[(R+1)][F][NB] (plane R = X2) | W_s[F][KS] | red[8][2*KMAX][NB] |
-// red2[2*KMAX][NB] | Hn_s[KMAX][NB] | meta[K+1+R][NB] + fu[NB] | cn_s[KMAX] | misc[32] | bars
+// red2[2*KMAX][NB] | Hn_s[KMAX][NB] | meta[NB][meta_stride] | cn_s[KMAX] | misc[32] | bars
 __host__ __device__ inline size_t cols_smem_floats(int F, int KS, int K, int R, int KMAX) {
   return (size_t)(R + 1) * F * NB + (size_t)F * KS + (size_t)CW * 2 * KMAX * NB + (size_t)2 * KMAX * NB + (size_t)KMAX * NB +
-         (size_t)(K + 1 + R + 1) * NB + KMAX + 32 + 2 * (2 * MAXCH + 2) + 4 + 2 * (MAXCH + 1);
+         (size_t)meta_stride(K, R) * NB + KMAX + 32 + 2 * (2 * MAXCH + 2) + 4 + 2 * (MAXCH + 1);
 }
 
 __device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, %0;" ::"n"(CCT) : "memory"); }
@@ -399,7 +421,7 @@ __global__ void __launch_bounds__(CTT, 1) k_cols_v1(ColsArgs p) {
   const int F = FT > 0 ? FT : p.F, K = p.K, NP = p.NP;
   constexpr int KS = (KMAX % 16 == 0) ? KMAX + 4 : KMAX;     // dictionary row stride in shared memory (= ks_of(K), the launcher sizes with it)
   const int R = RT > 0 ? RT : p.R;
-  const int MR = K + 1 + R;
+  const int MS = meta_stride(K, R);
   const int PS = F * NB;                                    // plane stride (floats); a plane is one bulk-contiguous block
   float* data = sm;
   float* W_s = data + (size_t)(R + 1) * PS;
@@ -407,7 +429,7 @@ __global__ void __launch_bounds__(CTT, 1) k_cols_v1(ColsArgs p) {
   float* red2 = red + CW * 2 * KMAX * NB;
   float* Hn_s = red2 + 2 * KMAX * NB;
   float* meta = Hn_s + KMAX * NB;                           // H_old [K][NB] | g [NB] | Vs_w [R][NB]   (one bulk copy)
-  float* cn_s = meta + (MR + 1) * NB;
+  float* cn_s = meta + MS * NB;
   float* misc = cn_s + KMAX;
   uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(misc + 32) + 7) & ~(uintptr_t)7);
   uint64_t* full = bars;                                    // [MAXCH] chunk j of the tile has landed
@@ -442,8 +464,8 @@ __global__ void __launch_bounds__(CTT, 1) k_cols_v1(ColsArgs p) {
     for (int t = t_hi - 1; t >= t_lo; --t, ++it) {
       if (it > 0) mbar_wait(mempty, (it - 1) & 1);
       if (lane == 0) {
-        mbar_expect_tx(mfull, (uint32_t)MR * NB * 4);
-        bulk_g2s(meta, p.Mt + (size_t)t * MR * NB, (uint32_t)MR * NB * 4, mfull);
+        mbar_expect_tx(mfull, (uint32_t)MS * NB * 4);
+        bulk_g2s(meta, p.Mt + (size_t)t * MS * NB, (uint32_t)MS * NB * 4, mfull);
       }
       for (int j = 0; j < NCH; ++j) {
         if (it > 0) mbar_wait(empty + j, (it - 1) & 1);
@@ -480,18 +502,19 @@ __global__ void __launch_bounds__(CTT, 1) k_cols_v1(ColsArgs p) {
       if (lane == 0) { mbar_arrive(mempty); for (int j = 0; j < NCH; ++j) mbar_arrive(empty + j); }
       continue;
     }
-    const float gg = meta[K * NB + n];
+    const float* mrec = meta + n * MS;                      // record of this thread's frame: H_old | g | multiplicities
+    const float gg = mrec[K];
     float hk[KMAX];
 #pragma unroll
-    for (int k = 0; k < KMAX; ++k) hk[k] = (k < K) ? meta[k * NB + n] : 0.f;
+    for (int k = 0; k < KMAX; ++k) hk[k] = (k < K) ? mrec[k] : 0.f;
     // multiplicities of the slots of this column: registers when R is a compile-time constant
     float wr[RT > 0 ? RT : 1];
     if (RT > 0) {
 #pragma unroll
-      for (int r = 0; r < RT; ++r) wr[r] = meta[(K + 1 + r) * NB + n];
+      for (int r = 0; r < RT; ++r) wr[r] = mrec[K + 1 + r];
     }
-    const float* wsm = meta + (K + 1) * NB + n;
-    auto wgt = [&](int r) -> float { return RT > 0 ? wr[RT > 0 ? r : 0] : wsm[r * NB]; };
+    const float* wsm = mrec + K + 1;
+    auto wgt = [&](int r) -> float { return RT > 0 ? wr[RT > 0 ? r : 0] : wsm[r]; };
 
     if (b != cur_b) {                                       // new utterance: dictionary -> smem, column norms
       cur_b = b;
@@ -586,7 +609,7 @@ __global__ void __launch_bounds__(CTT, 1) k_cols_v1(ColsArgs p) {
       float nu = 0.f, de = 0.f;
 #pragma unroll
       for (int w8 = 0; w8 < CW; ++w8) { nu += red[w8 * 2 * KMAX * NB + tid]; de += red[w8 * 2 * KMAX * NB + KMAX * NB + tid]; }
-      Hn_s[tid] = (k < K) ? meta[tid] * sqrtf(nu / de) : 0.f;
+      Hn_s[tid] = (k < K) ? meta[(tid & (NB - 1)) * MS + k] * sqrtf(nu / de) : 0.f;
     }
     bar_compute();
     float hn[KMAX];
@@ -754,18 +777,18 @@ struct GenArgs {
 };
 constexpr int GT = 256;
 __host__ __device__ inline size_t gen_smem_floats(int F, int KS, int K, int R) {
-  return (size_t)F * KS + (size_t)2 * F * NB + (size_t)(K + 1 + R) * NB + (size_t)K * NB + 32 + 8 * 2 * NB + 32 + 16;
+  return (size_t)F * KS + (size_t)2 * F * NB + (size_t)meta_stride(K, R) * NB + (size_t)K * NB + 32 + 8 * 2 * NB + 32 + 16;
 }
 
 template <int KMAX>
 __global__ void __launch_bounds__(GT, 2) k_cols_gen(GenArgs p) {
   extern __shared__ __align__(16) float sg[];
-  const int F = p.F, K = p.K, KS = p.KS, NP = p.NP, R = p.R, MR = K + 1 + R, T8 = NP / NB;
+  const int F = p.F, K = p.K, KS = p.KS, NP = p.NP, R = p.R, MS = meta_stride(K, R), T8 = NP / NB;
   float* W_s = sg;                                          // [F][KS]
   float* a_s = W_s + (size_t)F * KS;                        // [F][NB]  X2 * s2 of the H pass
   float* s1_s = a_s + (size_t)F * NB;                       // [F][NB]
   float* meta = s1_s + (size_t)F * NB;                      // H_old [K][NB] | g [NB] | multiplicities [R][NB]
-  float* Hn_s = meta + (size_t)MR * NB;                     // [K][NB]
+  float* Hn_s = meta + (size_t)MS * NB;                     // [K][NB]
   float* cn_s = Hn_s + (size_t)K * NB;                      // [32]
   float* red = cn_s + 32;                                   // [8 warps][2][NB]
   float* misc = red + 8 * 2 * NB;                           // [32]
@@ -777,7 +800,7 @@ __global__ void __launch_bounds__(GT, 2) k_cols_gen(GenArgs p) {
     const int b = p.frame_utt[(size_t)t * NB];
     if (b < 0) { if (tid == 0) p.cost_part[t] = 0.f; continue; }
     __syncthreads();                                        // previous tile is done with the shared arrays
-    for (int i = tid; i < MR * NB; i += GT) meta[i] = __ldg(p.Mt + (size_t)t * MR * NB + i);
+    for (int i = tid; i < MS * NB; i += GT) meta[i] = __ldg(p.Mt + (size_t)t * MS * NB + i);
     if (b != cur_b) {
       cur_b = b;
       cur_fo = p.frame_off[b];
@@ -799,13 +822,14 @@ __global__ void __launch_bounds__(GT, 2) k_cols_gen(GenArgs p) {
       for (int i = tid; i < F * K; i += GT) { const int ff = i / K, k = i - ff * K; wdst[i] = W_s[ff * KS + k] / cn_s[k]; }
     }
     const bool valid = p.frame_utt[(size_t)t * NB + n] >= 0;
-    const float gg = meta[K * NB + n];
-    const float* wts = meta + (K + 1) * NB + n;
+    const float* mrec = meta + n * MS;                      // record of this thread's frame
+    const float gg = mrec[K];
+    const float* wts = mrec + K + 1;
     const float* vs0 = p.Vs + (size_t)t * F * NB + n;       // + f*NB + r*slab
     const float* x2p = p.X2t + (size_t)t * F * NB + n;
     float hk[KMAX];
 #pragma unroll
-    for (int k = 0; k < KMAX; ++k) hk[k] = (k < K) ? meta[k * NB + n] : 0.f;
+    for (int k = 0; k < KMAX; ++k) hk[k] = (k < K) ? mrec[k] : 0.f;
     auto dot_w = [&](const float* wrow, const float (&h)[KMAX]) -> float {
       float vb0 = 0.f, vb1 = 0.f;
 #pragma unroll
@@ -823,8 +847,8 @@ __global__ void __launch_bounds__(GT, 2) k_cols_gen(GenArgs p) {
       const float* vs = vs0 + (size_t)f * NB;
       float s1 = 0.f, s2 = 0.f;
       int r = 0;
-      for (; r + 1 < R; r += 2) pair_acc(gg, vb, __ldg(vs + r * slab), __ldg(vs + (r + 1) * slab), wts[r * NB], wts[(r + 1) * NB], s1, s2);
-      if (r < R) single_acc(gg, vb, __ldg(vs + r * slab), wts[r * NB], s1, s2);
+      for (; r + 1 < R; r += 2) pair_acc(gg, vb, __ldg(vs + r * slab), __ldg(vs + (r + 1) * slab), wts[r], wts[r + 1], s1, s2);
+      if (r < R) single_acc(gg, vb, __ldg(vs + r * slab), wts[r], s1, s2);
       a_s[f * NB + n] = __ldg(x2p + (size_t)f * NB) * s2;
       s1_s[f * NB + n] = s1;
     }
@@ -840,7 +864,7 @@ __global__ void __launch_bounds__(GT, 2) k_cols_gen(GenArgs p) {
         nu1 = fmaf(w1, a_s[(f + 1) * NB + n], nu1); de1 = fmaf(w1, s1_s[(f + 1) * NB + n], de1);
       }
       if (f < F) { const float w0 = W_s[f * KS + k]; nu0 = fmaf(w0, a_s[f * NB + n], nu0); de0 = fmaf(w0, s1_s[f * NB + n], de0); }
-      Hn_s[tid] = meta[tid] * sqrtf((nu0 + nu1) / (de0 + de1));
+      Hn_s[tid] = meta[n * MS + k] * sqrtf((nu0 + nu1) / (de0 + de1));
     }
     __syncthreads();
     float hn[KMAX];
@@ -864,13 +888,13 @@ __global__ void __launch_bounds__(GT, 2) k_cols_gen(GenArgs p) {
         const float a = fmaf(gg, va, vb), c = fmaf(gg, vc, vb);
         const float ip = rcp_fast(a * c);
         const float ia = c * ip, ic = a * ip;
-        const float ua = wts[r * NB] * va * ia, uc = wts[(r + 1) * NB] * vc * ic;
+        const float ua = wts[r] * va * ia, uc = wts[r + 1] * vc * ic;
         t1 += ua + uc;
         t2 = fmaf(ua, ia, fmaf(uc, ic, t2));
       }
       if (r < R) {
         const float va = __ldg(vs + r * slab);
-        const float ia = rcp_fast(fmaf(gg, va, vb)), ua = wts[r * NB] * va * ia;
+        const float ia = rcp_fast(fmaf(gg, va, vb)), ua = wts[r] * va * ia;
         t1 += ua;
         t2 = fmaf(ua, ia, t2);
       }
@@ -899,12 +923,12 @@ __global__ void __launch_bounds__(GT, 2) k_cols_gen(GenArgs p) {
       int r = 0;
       for (; r + 1 < R; r += 2) {
         const float a = fmaf(gnew, __ldg(vs + r * slab), vb), c = fmaf(gnew, __ldg(vs + (r + 1) * slab), vb);
-        const float wa = wts[r * NB], wc = wts[(r + 1) * NB];
+        const float wa = wts[r], wc = wts[r + 1];
         sl = fmaf(wa, lg2_fast(a), fmaf(wc, lg2_fast(c), sl));
         sr = fmaf(fmaf(wa, c, wc * a), rcp_fast(a * c), sr);
       }
       if (r < R) {
-        const float a = fmaf(gnew, __ldg(vs + r * slab), vb), wa = wts[r * NB];
+        const float a = fmaf(gnew, __ldg(vs + r * slab), vb), wa = wts[r];
         sl = fmaf(wa, lg2_fast(a), sl);
         sr = fmaf(wa, rcp_fast(a), sr);
       }
@@ -993,7 +1017,7 @@ inline int ks_of(int K) { int ks = kmax_of(K); return (ks % 16 == 0) ? ks + 4 : 
 
 template <int KMAX>
 int32_t launch_v1_k(const gvn_batch* b, int R, const ColsArgs& a, size_t smem, int grid, cudaStream_t st) {
-  float* Wpart = const_cast<float*>(a.Mt) + (size_t)(b->K + 1 + b->R_cap) * b->NP;     // behind the column data (mstep_v1_workspace_bytes)
+  float* Wpart = const_cast<float*>(a.Mt) + (size_t)meta_stride(b->K, b->R_cap) * b->NP;     // behind the column data (mstep_v1_workspace_bytes)
   int32_t rc;
   if (R == 10) rc = (KMAX == 12 && b->K == 10) ? launch_w<KMAX, 10, (KMAX == 12 ? 10 : 0)>(b, R, a.Mt, Wpart, st) : launch_w<KMAX, 10>(b, R, a.Mt, Wpart, st);
   else rc = launch_w<KMAX, 0>(b, R, a.Mt, Wpart, st);
@@ -1025,7 +1049,7 @@ bool mstep_v1_supported(const gvn_batch* b, int R) {
 // workspace of variant 1: the column data in tile order + the partial sums of a frame-split W sweep
 size_t mstep_v1_workspace_bytes(const gvn_batch* b) {
   const int ns = w_nsplit(b);
-  return ((size_t)(b->K + 1 + b->R_cap) * b->NP + (ns > 1 ? (size_t)b->B * ns * b->F * b->K * 2 : 0)) * sizeof(float);
+  return ((size_t)meta_stride(b->K, b->R_cap) * b->NP + (ns > 1 ? (size_t)b->B * ns * b->F * b->K * 2 : 0)) * sizeof(float);
 }
 
 int32_t launch_mstep_v1(const gvn_batch* b, int R, float* cost_part, float* Mt, cudaStream_t st) {
@@ -1060,7 +1084,7 @@ int32_t launch_mstep_v1(const gvn_batch* b, int R, float* cost_part, float* Mt, 
     }
   }
   // generic shapes: bulk-copy W sweep (runtime R) + L2-resident column sweep
-  float* Wpart = Mt + (size_t)(b->K + 1 + b->R_cap) * b->NP;
+  float* Wpart = Mt + (size_t)meta_stride(b->K, b->R_cap) * b->NP;
   rc = b->K <= 16 ? launch_w<16, 0>(b, R, Mt, Wpart, st) : launch_w<32, 0>(b, R, Mt, Wpart, st);
   if (rc) return rc;
   GenArgs a;
