@@ -853,18 +853,39 @@ __global__ void __launch_bounds__(GT, 2) k_cols_gen(GenArgs p) {
       s1_s[f * NB + n] = s1;
     }
     __syncthreads();
-    // H update: thread (k, n) finishes  H <- H * sqrt( (W^T (X2 s2)) / (W^T s1) )
-    if (tid < K * NB) {
-      const int k = tid >> 3;
-      float nu0 = 0.f, nu1 = 0.f, de0 = 0.f, de1 = 0.f;
-      int f = 0;
-      for (; f + 1 < F; f += 2) {
-        const float w0 = W_s[f * KS + k], w1 = W_s[(f + 1) * KS + k];
-        nu0 = fmaf(w0, a_s[f * NB + n], nu0); de0 = fmaf(w0, s1_s[f * NB + n], de0);
-        nu1 = fmaf(w1, a_s[(f + 1) * NB + n], nu1); de1 = fmaf(w1, s1_s[(f + 1) * NB + n], de1);
+    // H update  H <- H * sqrt( (W^T (X2 s2)) / (W^T s1) ): thread = (slice of the frequency rows, group of four dictionary
+    // columns, frame) with eight accumulators -- one 16-byte load of W and two scalar loads per eight multiply-adds --
+    // then the slices are summed through the (now free) a_s array
+    {
+      const int KQ = (K + 3) / 4, combos = KQ * NB, nfs = GT / combos;
+      const int fs = tid / combos, rem = tid - fs * combos, kq = rem / NB, nn = rem & (NB - 1);
+      float nu[4] = {0.f, 0.f, 0.f, 0.f}, de[4] = {0.f, 0.f, 0.f, 0.f};
+      if (fs < nfs) {
+        for (int f = fs; f < F; f += nfs) {
+          const float4 w4 = *reinterpret_cast<const float4*>(W_s + f * KS + 4 * kq);     // columns beyond K are zero (KS >= KMAX)
+          const float av = a_s[f * NB + nn], sv = s1_s[f * NB + nn];
+          nu[0] = fmaf(w4.x, av, nu[0]); de[0] = fmaf(w4.x, sv, de[0]);
+          nu[1] = fmaf(w4.y, av, nu[1]); de[1] = fmaf(w4.y, sv, de[1]);
+          nu[2] = fmaf(w4.z, av, nu[2]); de[2] = fmaf(w4.z, sv, de[2]);
+          nu[3] = fmaf(w4.w, av, nu[3]); de[3] = fmaf(w4.w, sv, de[3]);
+        }
       }
-      if (f < F) { const float w0 = W_s[f * KS + k]; nu0 = fmaf(w0, a_s[f * NB + n], nu0); de0 = fmaf(w0, s1_s[f * NB + n], de0); }
-      Hn_s[tid] = meta[n * MS + k] * sqrtf((nu0 + nu1) / (de0 + de1));
+      __syncthreads();                                      // everybody has read a_s / s1_s
+      float* part = a_s;                                    // [nfs][4 KQ][NB][2]
+      if (fs < nfs) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float* d = part + (((size_t)fs * 4 * KQ + 4 * kq + i) * NB + nn) * 2;
+          d[0] = nu[i]; d[1] = de[i];
+        }
+      }
+      __syncthreads();
+      if (tid < K * NB) {
+        const int k = tid / NB;
+        float sn = 0.f, sd_ = 0.f;
+        for (int q = 0; q < nfs; ++q) { const float* d = part + (((size_t)q * 4 * KQ + k) * NB + n) * 2; sn += d[0]; sd_ += d[1]; }
+        Hn_s[tid] = meta[n * MS + k] * sqrtf(sn / sd_);
+      }
     }
     __syncthreads();
     float hn[KMAX];
@@ -1043,7 +1064,8 @@ bool mstep_v1_supported(const gvn_batch* b, int R) {
   if (b->X2t == nullptr || b->K > 32) return false;
   if (v1_staged(b, R)) return true;
   const size_t wstage = (size_t)w_stage_floats(b->K, R) * 4;
-  return 2 * wstage <= 200 * 1024 && gen_smem_floats(b->F, ks_gen(b->K), b->K, R) * 4 <= 227 * 1024;
+  // (the generic sweep sums its frequency slices through 2048 floats of the a_s / s1_s arrays: 2 * F * 8 floats)
+  return b->F >= 128 && 2 * wstage <= 200 * 1024 && gen_smem_floats(b->F, ks_gen(b->K), b->K, R) * 4 <= 227 * 1024;
 }
 
 // workspace of variant 1: the column data in tile order + the partial sums of a frame-split W sweep
