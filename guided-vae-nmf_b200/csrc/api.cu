@@ -107,7 +107,7 @@ int32_t gvn_estep(const gvn_batch* batch, const void* packed, int32_t burnin, in
   const int32_t prec = precision & ~GVN_PREC_XV_CURRENT;
   if (prec == GVN_PREC_FP32)
     return launch_estep_simt(batch, packed, burnin, R, var_RW, noise, trace, (cudaStream_t)stream);
-  if (prec == GVN_PREC_F16X3 || prec == GVN_PREC_F16)
+  if (prec == GVN_PREC_F16)
     return launch_estep_tc(batch, packed, burnin, R, var_RW, noise, trace, precision, (cudaStream_t)stream);
   return fail(GVN_E_INVALID, "unknown precision %d", precision);
 }

@@ -182,7 +182,8 @@ __global__ void __launch_bounds__(NT, 2) k_estep_simt(EstepArgs p) {
               }
             }
             if (vs_out != nullptr)    // column-tile order; nb is a multiple of 4, so the four frames stay adjacent
-              *reinterpret_cast<float4*>(vs_out + tile_off(f, nb, F)) = make_float4(vs[0], vs[1], vs[2], vs[3]);
+              *reinterpret_cast<float4*>(vs_out + tile_off(f, nb, F)) =      // GVN_VS_MAX: a slot never holds inf (include/gvn.h)
+                  make_float4(fminf(vs[0], GVN_VS_MAX), fminf(vs[1], GVN_VS_MAX), fminf(vs[2], GVN_VS_MAX), fminf(vs[3], GVN_VS_MAX));
           }
         }
       }

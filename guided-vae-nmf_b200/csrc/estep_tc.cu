@@ -1,4 +1,4 @@
-// E-step, tensor-core variant (GVN_PREC_F16 / GVN_PREC_F16X3): tcgen05.mma with the accumulators
+// E-step, tensor-core variant (GVN_PREC_F16): tcgen05.mma with the accumulators
 // and the activation operand in TMEM, weights in shared memory.  See DESIGN.md section 5.
 //
 // This file currently holds: the weight packing into UMMA operand images, and

@@ -423,7 +423,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_estep_tc(const __grid_constant_
                 const float q = qn * __uint_as_float(0x7f000000u - (pb & 0x7f800000u));       // qn * 2^-e
                 Nn = fmaf(q, Pm, Nn * m);
                 Pm *= m;
-                if (STORE && valid) { st_stream(vo + (2 * j) * GVN_VS_TILE, v0); st_stream(vo + (2 * j + 1) * GVN_VS_TILE, v1); }
+                if (STORE && valid) { st_stream(vo + (2 * j) * GVN_VS_TILE, fminf(v0, GVN_VS_MAX)); st_stream(vo + (2 * j + 1) * GVN_VS_TILE, fminf(v1, GVN_VS_MAX)); }
               }
               es -= 127 * 8;
               sl += lg2_approx(Pm);
@@ -442,7 +442,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_estep_tc(const __grid_constant_
                 const float qn = fmaf(__uint_as_float(w0), b, __uint_as_float(w1) * a);      // X2 = the whole word (k_pack_xv)
                 sr = fmaf(qn, rcp_approx(pr), sr);
               }
-              if (STORE && valid) { st_stream(vo + (2 * j) * GVN_VS_TILE, v0); st_stream(vo + (2 * j + 1) * GVN_VS_TILE, v1); }
+              if (STORE && valid) { st_stream(vo + (2 * j) * GVN_VS_TILE, fminf(v0, GVN_VS_MAX)); st_stream(vo + (2 * j + 1) * GVN_VS_TILE, fminf(v1, GVN_VS_MAX)); }
             }
             }
           } else {                                         // ragged tail of the spectrum (F = 513: one bin)
@@ -458,7 +458,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_estep_tc(const __grid_constant_
                 sl += lg2_approx(a);
                 sr = fmaf(__uint_as_float(w0), rcp_approx(a), sr);
               }
-              if (STORE && valid) st_stream(vo + j * GVN_VS_TILE, v0);
+              if (STORE && valid) st_stream(vo + j * GVN_VS_TILE, fminf(v0, GVN_VS_MAX));
             }
           }
           if (ENERGY) {
@@ -626,8 +626,7 @@ int32_t launch_estep_tc(const gvn_batch* b, const void* packed, int burnin, int 
                         const gvn_trace* tr, int precision, cudaStream_t st) {
   const bool xv_current = (precision & GVN_PREC_XV_CURRENT) != 0;
   precision &= ~GVN_PREC_XV_CURRENT;
-  if (precision != GVN_PREC_F16)
-    return fail(GVN_E_UNSUPPORTED_SHAPE, "precision %d: the hi/lo-split tensor-core chain is not built yet", precision);
+  GVN_REQUIRE(precision == GVN_PREC_F16, GVN_E_INVALID, "precision %d is not a tensor-core mode", precision);
   GVN_REQUIRE(b->XV != nullptr && b->Vs_w != nullptr, GVN_E_INVALID, "batch.XV / batch.Vs_w is NULL");
   DecoderLayout d = decoder_layout(b->L, 0, b->F);
   TcLayout t = tc_layout(b->L, b->F);

@@ -20,6 +20,7 @@
 #include <stdlib.h>
 
 #include "gvn_common.cuh"
+#include "tc_common.cuh"
 
 namespace gvn {
 
@@ -111,17 +112,7 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(s_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok = 0;
-  for (uint32_t spins = 0; !ok; ++spins) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(s_u32(bar)), "r"(parity) : "memory");
-    if (spins > (1u << 22)) __trap();       // a protocol bug must surface as an error, not a hang
-  }
-}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { tc::mbar_wait(bar, parity); }   // time-bounded spin: tc_common.cuh
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(s_u32(bar)) : "memory");
 }

@@ -1,5 +1,4 @@
-// Pieces shared by the two tensor-core chain kernels (estep_tc_chain.cu: one 128-frame tile per CTA;
-// estep_tc_sub.cu: two interleaved 64-frame sub-tiles per CTA): argument block, special-function wrappers,
+// Pieces of the tensor-core chain kernel (estep_tc_chain.cu: one 128-frame tile per CTA): argument block, special-function wrappers,
 // the XV packing pass and the TMA tensor map of XV.  Included inside an anonymous namespace of each file.
 #pragma once
 #include <cuda.h>
@@ -65,13 +64,14 @@ __global__ void __launch_bounds__(256) k_pack_xv(size_t n4, const float4* __rest
 // their spinning does not take issue slots from the epilogue warps of the same scheduler
 __device__ __forceinline__ void mbar_wait_idle(uint64_t* bar, uint32_t parity) {
   uint32_t ok = 0;
+  unsigned long long t0 = 0ull;
   for (uint32_t spins = 0; !ok; ++spins) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(20000u) : "memory");
-    if (spins > (1u << 16)) __trap();         // ~1 s: a protocol bug must fail fast
+    if (!ok) watchdog_poll(spins | 1023u, t0);       // every failed poll already slept up to ~20 us (tc_common.cuh)
   }
 }
 

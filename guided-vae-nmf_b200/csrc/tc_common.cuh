@@ -118,17 +118,31 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-// Bounded spin: a wait that cannot complete traps instead of hanging the GPU (a protocol bug
-// must surface as a launch error, never as a stuck device).
+// Watchdog of every barrier spin in this library: a wait that has not completed after GVN_WATCHDOG_NS of WALL time
+// (%globaltimer, sampled every 1024 failed polls) traps, so a protocol bug surfaces as a launch error instead of a
+// stuck device.  The bound is time, not a poll count -- the poll time of try_wait is implementation defined -- and it
+// is four orders of magnitude above the run time of any kernel here, profiler replay or sanitizer included.
+#ifndef GVN_WATCHDOG_NS
+#define GVN_WATCHDOG_NS 20000000000ull
+#endif
+__device__ __forceinline__ void watchdog_poll(uint32_t spins, unsigned long long& t0) {
+  if ((spins & 1023u) != 1023u) return;
+  unsigned long long now;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+  if (t0 == 0ull) t0 = now;
+  else if (now - t0 > GVN_WATCHDOG_NS) __trap();
+}
+// Spin on try_wait (a hardware-suspended wait, not a busy poll).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok = 0;
+  unsigned long long t0 = 0ull;
   for (uint32_t spins = 0; !ok; ++spins) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    if (spins > (1u << 22)) __trap();
+    if (!ok) watchdog_poll(spins, t0);
   }
 }
 

@@ -33,7 +33,7 @@ class EM:
     def __init__(self, niter=100):
         self.niter = niter
         self._R = None
-        self.precision = "fp32"        # "fp32" | "f16x3" | "f16"  (decoder arithmetic)
+        self.precision = "fp32"        # "fp32" | "f16"  (decoder arithmetic)
         self.mstep_variant = 1
         self.seed = None               # Philox seed; None -> derived from torch's seed
         self.replay = None             # dict(rand_W, rand_H, eps, u[, forced]) for parity runs

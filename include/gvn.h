@@ -41,7 +41,8 @@
  *                        following rejected steps) otherwise.  A Metropolis-Hastings reject repeats
  *                        the previous sample (mcem.py:280-289), so sum_r phi(Vs_r) of the reference
  *                        equals sum_slot Vs_w[slot] * phi(Vs[slot]); nothing is ever copied.
- *                        sum_slot Vs_w[slot][n] == R for every frame.
+ *                        sum_slot Vs_w[slot][n] == R for every frame.  Every stored value is finite (<= GVN_VS_MAX),
+ *                        also in slots of multiplicity 0.
  *    XV   [F][NP]    u32 per-bin constants of the tensor-core chain, one word per (f, n): low half =
  *                        bf16(Vb), high half such that the whole word read as f32 is nearest to X2.
  *                        Written by gvn_estep (unless GVN_PREC_XV_CURRENT) and kept current by gvn_mstep.
@@ -67,6 +68,9 @@ extern "C" {
 #define GVN_MAX_K 32            /* NMF rank limit */
 #define GVN_MAX_L 64            /* latent dimension limit */
 #define GVN_MAX_R_SLOTS 128     /* sample-slot limit of gvn_mstep_gain */
+#define GVN_VS_MAX 1e18f        /* gvn_estep clamps every speech variance it stores to this: a slot whose proposal was
+                                 * rejected because its decoder output overflowed (Vs_w = 0) must not put inf * 0 = NaN
+                                 * into the multiplicity-weighted sums of gvn_mstep / gvn_wiener */
 
 enum {
   GVN_OK = 0,
@@ -80,7 +84,8 @@ enum {
 /* arithmetic of the decoder contraction inside gvn_estep */
 enum {
   GVN_PREC_FP32 = 0,   /* CUDA-core fp32 FMA (bit-faithful mode, parity rtol 1e-4)           */
-  GVN_PREC_F16X3 = 1,  /* tcgen05 f16 hi/lo split, 3 MMAs, fp32 accumulate in TMEM (~fp32)   */
+  /* 1 is not assigned (a hi/lo-split fp32-parity tensor-core mode was planned under this value and never built:
+   * W3 as an f16 hi + lo pair is 270 KB, more than one SM's shared memory) */
   GVN_PREC_F16 = 2,    /* tcgen05 f16 operands, fp32 accumulate (11-bit mantissa, = TF32)    */
   /* flag, OR-ed into `precision`: batch->XV already matches (X2, Vb).  gvn_mstep rewrites XV next to
    * every Vb it writes, so inside the EM loop only the first gvn_estep has to pack it (the packing
@@ -132,8 +137,8 @@ const char* gvn_last_error(void);
 
 /* Decoder weights (models.py:107-121; state-dict keys decoder.hidden.{0,1}, decoder.
  * reconstruction).  W1 is (HID, L+y_dim) row-major as nn.Linear stores it.  The packed
- * image holds the transposed fp32 copies for the CUDA-core path and the f16 hi/lo UMMA
- * operand images for the tensor-core path. */
+ * image holds the transposed fp32 copies for the CUDA-core path and the f16 UMMA operand
+ * images for the tensor-core path. */
 size_t gvn_decoder_packed_bytes(int32_t L, int32_t y_dim, int32_t F, int32_t hidden);
 int32_t gvn_pack_decoder(const float* W1, const float* b1, const float* W2, const float* b2,
                          const float* W3, const float* b3, int32_t L, int32_t y_dim, int32_t F,
@@ -154,7 +159,7 @@ int32_t gvn_estep(const gvn_batch* batch /*HOST*/, const void* packed, int32_t b
 /* NMF / gain M-step: replaces EM.M_step + compute_expected_neg_log_like
  * (mcem.py:90-152, :68-70).  Updates W, H, g, Vb in place; cost_part receives one partial
  * sum per GVN_COST_TILE frames ([NP/8]); gvn_cost_reduce turns niter of them into cost[niter][B].
- * variant 0: straightforward schedule, any shape (the schedule the parity tests pin to the oracle).
+ * variant 0: straightforward schedule (IEEE divisions, logf), any shape.
  * variant 1 (default): bulk-copy W sweep + column sweep with the (R+1) x F x 8 tile staged once in
  * shared memory (K <= 12 at R = 10), or the generic L2-resident column sweep (K <= 32, R <= ~90);
  * falls back to 0 when neither fits. */

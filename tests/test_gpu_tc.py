@@ -164,3 +164,28 @@ def test_xv_kept_current_by_mstep(K, variant):
     np.testing.assert_allclose(lo.view(np.float32)[:, valid], vb[:, valid], rtol=2.0 ** -8)
     x2 = b.X2.cpu().numpy()
     np.testing.assert_allclose(xv.view(np.float32)[:, valid], x2[:, valid], rtol=2.0 ** -8, atol=1e-30)
+
+
+@pytest.mark.parametrize("prec", ["fp32", "f16"])
+def test_stored_speech_variance_is_clamped_to_a_finite_maximum(prec):
+    """A proposal whose decoder output overflows is rejected (acc_prob = -inf), but its slot (multiplicity 0) is still
+    multiplied into the weighted sums of the M-step: gvn_estep therefore never stores inf (GVN_VS_MAX, include/gvn.h)."""
+    from gvn import engine as E
+    from python.models.models import VariationalAutoencoder
+    torch.manual_seed(1)
+    F, L, N, R, burnin = 513, 16, 40, 3, 2
+    vae = VariationalAutoencoder([F, L, [128, 128]]).eval()
+    with torch.no_grad():
+        vae.decoder.reconstruction.bias.fill_(-3.0)
+        vae.decoder.reconstruction.bias[7] = 100.0          # exp(100) overflows fp32
+    dec = E.PackedDecoder(vae, "cuda:0")
+    b = E.Batch([N], F, 4, L, R, "cuda:0", with_complex=False)
+    b.X2.copy_(torch.rand(F, b.NP, device="cuda") + 1e-3)
+    E.init_nmf(b, 1e-8, generator=torch.Generator(device="cuda").manual_seed(2))
+    E.set_labels(b, dec, None)
+    E.estep(b, dec, burnin, R, 0.01, prec, seed=3)
+    torch.cuda.synchronize()
+    vs = b.Vs[:R].permute(0, 2, 1, 3).reshape(R, F, b.NP)[:, :, b.cols(0)]
+    assert bool(torch.isfinite(vs).all())
+    assert float(vs[:, 7].min()) == float(vs[:, 7].max()) == float(np.float32(1e18))
+    assert float(vs[:, :7].max()) < 1.0

@@ -23,7 +23,7 @@ enh = Enhancer(vae, cfg, "cuda:0")
 x, s, nz, labels = bench.make_inputs(B, 0)
 b = enh.prepare(list(x), labels, seed=0)
 tiles = (b.NP + 127) // 128
-buf = torch.zeros(tiles, 18, 16, dtype=torch.int64, device="cuda")
+buf = torch.zeros(tiles, 10, 16, dtype=torch.int64, device="cuda")    # [tile][warp][counter], as the kernel indexes it
 for it in range(3):
     E.estep(b, enh.dec, 30, 10, 0.01, "f16", seed=1, chain=it)
 torch.cuda.synchronize()
@@ -35,12 +35,12 @@ t1.record()
 torch.cuda.synchronize()
 lib.gvn_debug_profile_buffer(C.c_void_p(0))
 ms = t0.elapsed_time(t1)
-a = buf.cpu().numpy().astype(np.float64)[:, :16, :12]         # epilogue warps only
+a = buf.cpu().numpy().astype(np.float64)[:, :8, :12]          # epilogue warps only
 names = ["pre-hidden (put_z, noise, accept tail)", "wait L1 acc", "hidden0 math", "wait L2 acc", "hidden1 math", "wait chunk acc",
          "wait ring", "stage math", "energy barrier", "accept/other", "-", "-"]
 tot = a.sum(-1).mean()
 print("launch %.3f ms, %d tiles; mean cycles per epilogue warp %.0f (%.3f ms at 1.965 GHz)" % (ms, tiles, tot, tot / 1.965e6))
-for half, nm in ((slice(0, 4), "owner warps 0-3"), (slice(4, 8), "noise warps 4-7"), (slice(8, 16), "warps 8-15")):
+for half, nm in ((slice(0, 4), "owner warps 0-3"), (slice(4, 8), "noise warps 4-7")):
     m = a[:, half, :].mean((0, 1))
     print(nm)
     for i, nme in enumerate(names[:10]):

@@ -1,5 +1,5 @@
 """Times the E-step chain launch alone at the benchmark shape (run on the B200 box):
-GVN_TC_VARIANT=v python tools/estep_time.py [batch] [precision]"""
+python tools/estep_time.py [batch] [precision]"""
 import os
 import sys
 
@@ -29,5 +29,5 @@ for i in range(10):
 ev[10].record()
 torch.cuda.synchronize()
 ts = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(10))
-print("variant %s: chain (30+10 steps, %d frames) median %.4f ms  min %.4f ms; finite=%s" %
-      (os.environ.get("GVN_TC_VARIANT", "default"), b.NP, ts[5], ts[0], bool(torch.isfinite(b.Vs).all())))
+print("chain (30+10 steps, %d frames) median %.4f ms  min %.4f ms; finite=%s" %
+      (b.NP, ts[5], ts[0], bool(torch.isfinite(b.Vs).all())))
