@@ -216,28 +216,31 @@ def stft_geometry(T, fs, wlen_sec, hop_percent):
 _PINNED = {}
 
 
+def _grow_view(cache, key, shape, make):
+    """View of `shape` into a flat buffer kept per key; the buffer only grows (by at least a quarter, so that a list of
+    files with slowly growing lengths does not reallocate every batch).  Batches of a real file list all differ in
+    T_stride and NP: one buffer per distinct shape would pin memory in proportion to the length of the list."""
+    n = 1
+    for d in shape:
+        n *= int(d)
+    flat = cache.get(key)
+    if flat is None or flat.numel() < n:
+        flat = cache[key] = make(max(n, 0 if flat is None else flat.numel() * 5 // 4))
+    return flat[:n].view(*shape)
+
+
 def pinned_buffer(tag, shape, dtype=torch.float32):
-    """Page-locked staging buffer, allocated once per (tag, shape) and reused: cudaHostAlloc of tens of
-    megabytes per call costs more than the copy it serves."""
-    key = (tag, tuple(shape), dtype)
-    buf = _PINNED.get(key)
-    if buf is None:
-        buf = torch.zeros(*shape, dtype=dtype).pin_memory()
-        _PINNED[key] = buf
-    return buf
+    """Page-locked staging buffer, one per (tag, dtype), grown on demand and handed out as a view: cudaHostAlloc of
+    tens of megabytes per call costs more than the copy it serves, and keeping one buffer per shape leaks."""
+    return _grow_view(_PINNED, (tag, dtype), tuple(shape), lambda n: torch.zeros(n, dtype=dtype).pin_memory())
 
 
 _DEVBUF = {}
 
 
 def device_buffer(tag, shape, dtype, device):
-    """Device-side landing buffer of an upload, allocated once per (tag, shape) and reused."""
-    key = (tag, tuple(shape), dtype, str(device))
-    buf = _DEVBUF.get(key)
-    if buf is None:
-        buf = torch.empty(*shape, dtype=dtype, device=device)
-        _DEVBUF[key] = buf
-    return buf
+    """Device-side landing buffer of an upload, one per (tag, dtype, device), grown on demand (see pinned_buffer)."""
+    return _grow_view(_DEVBUF, (tag, dtype, str(device)), tuple(shape), lambda n: torch.empty(n, dtype=dtype, device=device))
 
 
 _CONST_I32 = {}

@@ -117,3 +117,19 @@ def test_labels_and_metric_match_oracle():
     s, n = rs.randn(1000), rs.randn(1000)
     e = 0.7 * s + 0.2 * n + 0.05 * np.random.RandomState(1).randn(1000)
     np.testing.assert_allclose(energy_ratios(e, s, n), O.energy_ratios(e, s, n), rtol=1e-12)
+
+
+def test_staging_buffers_grow_instead_of_accumulating():
+    """Staging buffers are kept per tag, not per shape: batches of a real file list all differ in T_stride / NP, and one
+    page-locked buffer per distinct shape would pin memory in proportion to the length of the list."""
+    import torch
+    cache = {}
+    make = lambda n: torch.zeros(n)
+    a = engine._grow_view(cache, "wav", (3, 5), make)
+    b = engine._grow_view(cache, "wav", (2, 4), make)
+    assert a.data_ptr() == b.data_ptr() and tuple(b.shape) == (2, 4) and b.is_contiguous()
+    c = engine._grow_view(cache, "wav", (10, 10), make)
+    assert tuple(c.shape) == (10, 10) and len(cache) == 1 and cache["wav"].numel() >= 100
+    for k in range(200):                                   # 200 distinct shapes: still one buffer
+        engine._grow_view(cache, "wav", (7, 100 + k), make)
+    assert len(cache) == 1 and cache["wav"].numel() < 2 * 7 * 300
