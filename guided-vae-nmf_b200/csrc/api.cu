@@ -44,6 +44,8 @@ int32_t launch_istft(const gvn_batch*, const float*, int, int, const int32_t*, f
 int32_t launch_dense(const float*, const float*, const float*, int, const float*, int, const float*, const float*, float,
                      int, int, int, float*, cudaStream_t);
 void set_profile_buffer(void*);
+size_t speech_labels_workspace_bytes(const gvn_batch*);
+int32_t launch_speech_labels(const gvn_batch*, const float*, int, int, float, float*, void*, cudaStream_t);
 int32_t launch_energy_ratios(const float*, const float*, const float*, int, int, const int32_t*, double*, cudaStream_t);
 int32_t launch_selftest_umma(const float*, const float*, int, int, int, float*, cudaStream_t);
 int32_t launch_pack_decoder(const float*, const float*, const float*, const float*, const float*, const float*, int, int,
@@ -200,6 +202,18 @@ int32_t gvn_spp_mask(const gvn_batch* batch, float fixed_smooth, float prob_smoo
   GVN_REQUIRE(batch->X2 && (soft || hard), GVN_E_INVALID, "NULL pointer");
   GVN_REQUIRE(prior > 0.f && prior < 1.f && n_init >= 0, GVN_E_INVALID, "prior=%g n_init=%d", (double)prior, n_init);
   return launch_spp_mask(batch, fixed_smooth, prob_smooth, prior, snr_opt_db, n_init, soft, hard, (cudaStream_t)stream);
+}
+
+size_t gvn_speech_labels_workspace_bytes(const gvn_batch* batch) { return batch ? speech_labels_workspace_bytes(batch) : 0; }
+
+int32_t gvn_speech_labels(const gvn_batch* batch, const float* S, int32_t from_power, int32_t vad, float quantile_fraction,
+                          float quantile_weight, float* y, void* workspace, void* stream) {
+  int32_t rc = check_batch(batch, false);
+  if (rc) return rc;
+  GVN_REQUIRE(S && y && workspace, GVN_E_INVALID, "NULL pointer");
+  GVN_REQUIRE(quantile_fraction > 0.f && quantile_fraction <= 1.f, GVN_E_INVALID, "quantile_fraction=%g outside (0,1]", (double)quantile_fraction);
+  GVN_REQUIRE(quantile_weight > 0.f && quantile_weight <= 1.f, GVN_E_INVALID, "quantile_weight=%g outside (0,1]", (double)quantile_weight);
+  return launch_speech_labels(batch, S, from_power, vad, quantile_fraction, y, workspace, (cudaStream_t)stream);
 }
 
 int32_t gvn_init_nmf(const gvn_batch* batch, const float* rand_W, const float* rand_H, float eps, void* stream) {

@@ -55,6 +55,8 @@ SIGNATURES = {
     "gvn_dense": (_i, [_p, _p, _p, _i, _p, _i, _p, _p, C.c_float, _i, _i, _i, _p, _p]),
     "gvn_spp_mask": (_i, [C.POINTER(GvnBatch), C.c_float, C.c_float, C.c_float, C.c_float, _i, _p, _p, _p]),
     "gvn_init_nmf": (_i, [C.POINTER(GvnBatch), _p, _p, C.c_float, _p]),
+    "gvn_speech_labels_workspace_bytes": (C.c_size_t, [C.POINTER(GvnBatch)]),
+    "gvn_speech_labels": (_i, [C.POINTER(GvnBatch), _p, _i, _i, C.c_float, C.c_float, _p, _p, _p]),
     "gvn_energy_ratios": (_i, [_p, _p, _p, _i, _i, _p, _p, _p]),
     "gvn_selftest_umma": (_i, [_p, _p, _i, _i, _i, _p, _p]),
     "gvn_debug_profile_buffer": (None, [_p]),

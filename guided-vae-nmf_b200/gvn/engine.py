@@ -293,6 +293,17 @@ def stft_into(batch, wav_dev, T, T_stride, n_fft, hop, end_pad):
     return T_d, ep_d
 
 
+def stft_to(batch, wav_dev, T, T_stride, n_fft, hop, end_pad, Xc_out, X2_out):
+    """STFT of B waveforms with the geometry of `batch` into caller-supplied planes ([F][NP][2] and [F][NP] f32) instead
+    of the batch's own Xc / X2: the clean-speech spectrogram the oracle labels are made from."""
+    lib = _lib.load()
+    batch.struct()
+    alias = GvnBatch.from_buffer_copy(batch._struct)
+    alias.Xc, alias.X2 = Xc_out.data_ptr(), X2_out.data_ptr()
+    check(lib.gvn_stft_power(C.byref(alias), _ptr(wav_dev), T_stride, _ptr(const_i32(T, batch.device)),
+                             _ptr(const_i32(end_pad, batch.device)), n_fft, hop, _stream()))
+
+
 def istft_from(batch, S, out_len, T_stride, n_fft, hop):
     """S: [F][NP][2] f32 on device -> (B, T_stride) f32 waveforms on device."""
     lib = _lib.load()
@@ -355,6 +366,18 @@ def classify(batch, classifier, mean=None, std=None, eps=0.0, hard=True):
             h = dense(W, b, h, None, "relu", batch.NP)
     W, b = _linear_params(classifier.output_layer, batch.device)
     return dense(W, b, h, None, "hard" if hard else "sigmoid", batch.NP)
+
+
+def speech_labels(batch, S, vad=False, quantile_fraction=0.98, quantile_weight=0.999, from_power=False):
+    """Oracle guide labels of the batch from the clean-speech STFT S ([F][NP][2] f32, or the power [F][NP] with
+    ``from_power``): clean_speech_IBM / clean_speech_VAD (python/processing/target.py:7-50) per utterance.
+    Returns [F][NP] (IBM) or [1][NP] (VAD) f32 on the device."""
+    lib = _lib.load()
+    y = torch.empty(1 if vad else batch.F, batch.NP, dtype=torch.float32, device=batch.device)
+    ws = torch.empty(lib.gvn_speech_labels_workspace_bytes(batch.struct()), dtype=torch.uint8, device=batch.device)
+    check(lib.gvn_speech_labels(batch.struct(), _ptr(S), int(bool(from_power)), int(bool(vad)), float(quantile_fraction),
+                                float(quantile_weight), _ptr(y), _ptr(ws), _stream()))
+    return y
 
 
 def spp_mask(batch, fixed_smooth=0.8, prob_smooth=0.9, prior=0.5, snr_opt_db=15.0, n_init=10, want_soft=True):

@@ -63,8 +63,9 @@ def evaluate_file_list(enhancer, file_paths, processed_dir, output_dir, label_so
         raise ValueError("model %s and label_source %r do not go together" % (cfg.model, label_source))
     if label_source == "classifier" and enhancer.classifier is None:
         raise ValueError("label_source='classifier' needs an Enhancer built with a classifier")
-    if label_source == "timo":
-        enhancer.label_source = "timo"
+    if label_source in ("timo", "oracle_ibm", "oracle_vad"):
+        enhancer.label_source = label_source
+        enhancer.quantile_fraction, enhancer.quantile_weight = quantile_fraction, quantile_weight
     files = shard_list(list(file_paths), world, rank)
     groups = [files[i:i + batch_size] for i in range(0, len(files), batch_size)]
     oracle = label_source in ("oracle_ibm", "oracle_vad")
@@ -79,15 +80,10 @@ def evaluate_file_list(enhancer, file_paths, processed_dir, output_dir, label_so
             items = [f.result() for f in nxt]
             nxt = fetch(groups[gi + 1]) if gi + 1 < len(groups) else None        # disk reads of the next batch start now
             wavs = [it[0] for it in items]
-            labels = None
-            if oracle:
-                from python.processing.stft import stft
-                from python.processing.target import clean_speech_IBM, clean_speech_VAD
-                fn = clean_speech_IBM if label_source == "oracle_ibm" else clean_speech_VAD
-                kw = dict(fs=cfg.fs, wlen_sec=cfg.wlen_sec, win="hann", hop_percent=cfg.hop_percent, dtype="complex64")
-                labels = [fn(stft(it[1], **kw), quantile_fraction, quantile_weight).astype(np.uint8) for it in items]
             with torch.cuda.device(enhancer.device):
-                b = enhancer.prepare(wavs, labels, seed=seed + gi)
+                # oracle labels: the clean speech travels with the batch; STFT, ranking and threshold run on the device
+                up = enhancer.upload(wavs, clean=[it[1] for it in items] if oracle else None)
+                b = enhancer.prepare(None, None, seed=seed + gi, uploaded=up)
                 y_soft = y_hard = None
                 if cfg.model == "M2":
                     y_hard = b.y
@@ -110,7 +106,7 @@ def evaluate_file_list(enhancer, file_paths, processed_dir, output_dir, label_so
                 cols = b.cols(i)
                 ysi = None if ys is None else torch.t(ys[:, cols]).contiguous()   # (N, y_dim) as the scripts save them
                 if oracle and ysi is not None:
-                    ysi = labels[i].astype(np.float32)                            # oracle: the (y_dim, N) numpy mask itself (evaluate_M2_ibm.py:133, :170)
+                    ysi = ys[:, cols].numpy().astype(np.float32)                  # oracle: the (y_dim, N) numpy mask itself (evaluate_M2_ibm.py:133, :170)
                 yhi = None if yh is None else torch.t(yh[:, cols]).contiguous()
                 pending_w.append(writers.submit(_write_item, output_dir, fp, s_h[i, :T].numpy().copy(), n_h[i, :T].numpy().copy(),
                                                 cfg.fs, ysi, yhi))

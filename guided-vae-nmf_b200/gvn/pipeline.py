@@ -43,9 +43,13 @@ class McemConfig:
 class Enhancer:
     """Holds the packed model on one device and enhances batches of utterances."""
 
-    def __init__(self, vae, cfg, device, classifier=None, mean=None, std=None, label_source=None):
+    def __init__(self, vae, cfg, device, classifier=None, mean=None, std=None, label_source=None,
+                 quantile_fraction=0.999, quantile_weight=0.999):
         """``label_source`` for M2 when no labels are passed in: None = the classifier (evaluate_M2_ibm.py:121-131),
-        "timo" = the speech-presence-probability mask (:136-141; needs y_dim == F)."""
+        "timo" = the speech-presence-probability mask (:136-141; needs y_dim == F), "oracle_ibm" / "oracle_vad" = the
+        oracle labels of the clean speech uploaded with the batch (``clean=`` of :meth:`upload`, or the clean-speech
+        metric reference; :132-134, python/processing/target.py:7-50 with the scripts' quantiles 0.999 / 0.999)."""
+        self.quantile_fraction, self.quantile_weight = quantile_fraction, quantile_weight
         self.device = E._require_cuda(device)
         self.label_source = label_source
         self.cfg = cfg
@@ -59,7 +63,7 @@ class Enhancer:
             self.dec = E.PackedDecoder(vae, self.device)
         self._batches = {}          # batch state in HBM is allocated once per shape and reused (stream-ordered)
 
-    def upload(self, wavs, labels=None, refs=None, slot=0):
+    def upload(self, wavs, labels=None, refs=None, slot=0, clean=None):
         """Host -> device copy of one batch of inputs (pinned staging, async on the current stream): the
         waveforms and, for oracle-label M2, the (y_dim, N_b) label arrays.  Binary labels travel as one
         byte per bin and are widened on the device.  ``refs`` = (clean speech, noise) arrays (B, T) for the
@@ -85,6 +89,11 @@ class Enhancer:
                 y = yd.float() if binary else yd
                 nbytes += host.numel() * host.element_size()
             out = dict(wav=wav, T=T, T_stride=T_stride, geo=geo, y=y, h2d_bytes=nbytes)
+            if clean is not None:                           # clean speech for the oracle labels (label_source "oracle_*")
+                cw, _, cs = E.upload_waveforms(clean, dev, tag="clean%d" % slot)
+                assert cs == T_stride, "clean speech and mixture must have the same lengths"
+                out["clean"] = cw
+                out["h2d_bytes"] += cw.numel() * 4
             if refs is not None:
                 for name, arr in zip(("ref_s", "ref_n"), refs):
                     host = E.pinned_buffer("%s%d" % (name, slot), (len(wavs), T_stride))
@@ -120,6 +129,14 @@ class Enhancer:
             if cfg.model == "M2":
                 if up["y"] is not None:
                     y = up["y"]
+                elif self.label_source in ("oracle_ibm", "oracle_vad"):
+                    clean = up.get("clean", up.get("ref_s"))
+                    if clean is None:
+                        raise ValueError("label_source=%r needs the clean speech of the batch (upload(..., clean=) or refs=)" % self.label_source)
+                    Sc = E.device_buffer("clean_Xc", (b.F, b.NP, 2), torch.float32, dev)
+                    P2 = E.device_buffer("clean_X2", (b.F, b.NP), torch.float32, dev)
+                    E.stft_to(b, clean, up["T"], up["T_stride"], nfft, hop, [g[2] for g in geo], Sc, P2)
+                    y = E.speech_labels(b, Sc, self.label_source == "oracle_vad", self.quantile_fraction, self.quantile_weight)
                 elif self.label_source == "timo":
                     b.y_soft, y = E.spp_mask(b)
                 else:

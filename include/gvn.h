@@ -213,6 +213,18 @@ int32_t gvn_dense(const float* W, const float* b, const float* in0, int32_t D0, 
 int32_t gvn_spp_mask(const gvn_batch* batch /*HOST*/, float fixed_smooth, float prob_smooth, float prior,
                      float snr_opt_db, int32_t n_init, float* soft, float* hard, void* stream);
 
+/* Oracle guide labels from the clean-speech STFT: replaces clean_speech_IBM / clean_speech_VAD
+ * (python/processing/target.py:7-27, :29-50; call sites scripts/evaluate_M2_ibm.py:132-134).  Per utterance: power
+ * |S conj(S)| (vad != 0: summed over frequency per frame), sorted descending, threshold = the last value whose share
+ * cumsum / sum is below quantile_fraction, label = power > threshold.  The float32 arithmetic follows numpy's order
+ * (sequential cumsum, pairwise sum, FMA product), so the labels equal the reference's bit for bit on the same S.
+ * S: [F][NP] c64 (from_power == 0) or the power itself, [F][NP] f32 (from_power != 0); y: [F][NP] f32 (vad == 0) or
+ * [NP] f32 (vad != 0), 0 on padding frames.  quantile_weight only softens the mask before it is rounded back
+ * (target.py:22-24): any value in (0, 1] gives the same labels; others are rejected. */
+size_t gvn_speech_labels_workspace_bytes(const gvn_batch* batch /*HOST*/);
+int32_t gvn_speech_labels(const gvn_batch* batch /*HOST*/, const float* S, int32_t from_power, int32_t vad,
+                          float quantile_fraction, float quantile_weight, float* y, void* workspace, void* stream);
+
 /* NMF initialisation W = max(rand, eps), H = max(rand, eps), g = 1, Vb = W@H, from caller
  * supplied uniforms (mcem.py:36-57); also fills padding frames with benign values. */
 int32_t gvn_init_nmf(const gvn_batch* batch /*HOST*/, const float* rand_W /*[B][F][K]*/,
