@@ -107,70 +107,102 @@ __global__ void __launch_bounds__(LT) k_label_sort(int F, int vad, const int32_t
   }
 }
 
-// numpy's pairwise summation (numpy/_core/src/umath/loops_utils.h.src: pairwise_sum), float32
-__device__ float np_pairwise_sum(const float* a, size_t n) {
-  // explicit stack instead of recursion: (offset, length, state) ; depth <= 40
-  struct Frame { size_t off, len; float left; int stage; };
-  Frame st[48];
-  int sp = 0;
-  st[0] = {0, n, 0.f, 0};
+// numpy's pairwise summation (numpy/_core/src/umath/loops_utils.h.src: pairwise_sum), float32, over a[0..n) in global
+// memory, by one warp.  The recursion (halves rounded down to a multiple of 8, leaves of <= 128 values summed with 8
+// interleaved accumulators) is an explicit stack that every lane walks in lockstep.  The leaf sums do not depend on one
+// another: the walk runs twice -- first it only collects the leaves, 32 at a time, and each lane sums one of them
+// (into `leaf`, global scratch); then it combines the stored leaf sums in the reference's order.
+constexpr int TCH = 2048;
+struct PwFrame { size_t off, len; float left; int stage; };
+
+__device__ __forceinline__ float np_leaf_sum(const float* __restrict__ p, size_t len) {
+  if (len < 8) {
+    float res = 0.f;
+    for (size_t i = 0; i < len; ++i) res = __fadd_rn(res, p[i]);
+    return res;
+  }
+  float r[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) r[j] = p[j];
+  size_t i = 8;
+  for (; i < len - (len % 8); i += 8) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = __fadd_rn(r[j], p[i + j]);
+  }
+  float res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])), __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+  for (; i < len; ++i) res = __fadd_rn(res, p[i]);
+  return res;
+}
+
+__device__ float np_pairwise_sum(const float* __restrict__ a, size_t n, float* __restrict__ leaf, int lane) {
   float ret = 0.f;
-  while (sp >= 0) {
-    Frame& f = st[sp];
-    if (f.len <= 128) {
-      const float* p = a + f.off;
-      float res;
-      if (f.len < 8) {
-        res = 0.f;
-        for (size_t i = 0; i < f.len; ++i) res = __fadd_rn(res, p[i]);
-      } else {
-        float r[8];
-        for (int j = 0; j < 8; ++j) r[j] = p[j];
-        size_t i = 8;
-        for (; i < f.len - (f.len % 8); i += 8)
-          for (int j = 0; j < 8; ++j) r[j] = __fadd_rn(r[j], p[i + j]);
-        res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])), __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
-        for (; i < f.len; ++i) res = __fadd_rn(res, p[i]);
+  for (int phase = 0; phase < 2; ++phase) {
+    PwFrame st[48];
+    int sp = 0;
+    st[0] = {0, n, 0.f, 0};
+    size_t n_leaf = 0;
+    size_t my_off = 0, my_len = 0;                          // phase 0: the leaf this lane sums in the current group of 32
+    while (sp >= 0) {
+      PwFrame& f = st[sp];
+      if (f.len <= 128) {
+        if (phase == 0) {
+          if ((int)(n_leaf & 31) == lane) { my_off = f.off; my_len = f.len; }
+          if ((n_leaf & 31) == 31) { leaf[n_leaf - 31 + lane] = np_leaf_sum(a + my_off, my_len); my_len = 0; }
+        } else {
+          ret = leaf[n_leaf];
+        }
+        ++n_leaf;
+        --sp;
+        continue;
       }
-      ret = res;
-      --sp;
-      continue;
+      size_t n2 = f.len / 2;
+      n2 -= n2 % 8;
+      if (f.stage == 0) {                                   // descend into the left half
+        f.stage = 1;
+        st[sp + 1] = {f.off, n2, 0.f, 0};
+        ++sp;
+      } else if (f.stage == 1) {                            // left half done: keep it, descend into the right half
+        f.left = ret;
+        f.stage = 2;
+        st[sp + 1] = {f.off + n2, f.len - n2, 0.f, 0};
+        ++sp;
+      } else {
+        ret = __fadd_rn(f.left, ret);
+        --sp;
+      }
     }
-    size_t n2 = f.len / 2;
-    n2 -= n2 % 8;
-    if (f.stage == 0) {                                     // descend into the left half
-      f.stage = 1;
-      st[sp + 1] = {f.off, n2, 0.f, 0};
-      ++sp;
-    } else if (f.stage == 1) {                              // left half done: keep it, descend into the right half
-      f.left = ret;
-      f.stage = 2;
-      st[sp + 1] = {f.off + n2, f.len - n2, 0.f, 0};
-      ++sp;
-    } else {
-      ret = __fadd_rn(f.left, ret);
-      --sp;
+    if (phase == 0) {
+      if ((n_leaf & 31) != 0 && lane < (int)(n_leaf & 31)) leaf[(n_leaf & ~(size_t)31) + lane] = np_leaf_sum(a + my_off, my_len);
+      __syncwarp();
+      __threadfence_block();
     }
   }
   return ret;
 }
 
 // threshold of one utterance: the last sorted value whose Lorenz share is below the quantile (target.py:19-21).
-// One warp per utterance: lane 0 carries the sequential float32 sums, the warp stages the sorted values through shared
-// memory in coalesced chunks.  The shares fl(cumsum / total) never decrease, so the first failure ends the prefix; the
-// exact division is only evaluated near the crossing (a cumsum safely below qf * total cannot fail the test).
-constexpr int TCH = 2048;
+// One warp per utterance: lane 0 carries the sequential float32 cumsum, the warp stages the sorted values through shared
+// memory in coalesced chunks.  The shares fl(cumsum / total) never decrease, so the first failure ends the prefix.
 __global__ void __launch_bounds__(32) k_label_threshold(int F, int vad, float qf, const int32_t* __restrict__ n_frames,
                                                         const size_t* __restrict__ seg_off, const uint32_t* __restrict__ keys,
-                                                        float* __restrict__ thr) {
-  __shared__ float buf[TCH];
+                                                        uint32_t* __restrict__ tmp, float* __restrict__ thr) {
+  __shared__ __align__(16) float buf[TCH];
   const int b = blockIdx.x, lane = threadIdx.x;
   const size_t n = (size_t)n_frames[b] * (vad ? 1 : F);
   const float* a = reinterpret_cast<const float*>(keys + seg_off[b]);
-  float total = 0.f;
-  if (lane == 0) total = np_pairwise_sum(a, n);
-  total = __shfl_sync(0xffffffffu, total, 0);
-  const float safe = qf * total * 0.9999f;                  // acc < safe  ==>  fl(acc / total) < qf  (qf in (0, 1], positive sums)
+  const float total = np_pairwise_sum(a, n, reinterpret_cast<float*>(tmp + seg_off[b]), lane);   // the sort's second buffer is free now
+  // The share test fl(acc / total) < qf is monotone in acc: the largest float `amax` that passes it is found once by
+  // bisection on the bit pattern (31 exact divisions), and the scan itself only compares acc <= amax -- the same
+  // decisions as the reference's division per element, without a division per element.
+  float amax = __int_as_float(0x7fc00000);
+  if (__fdiv_rn(0.f, total) < qf) {
+    uint32_t lo = 0u, hi = 0x7f800000u;                     // passes | fails (inf / total is not below qf <= 1)
+    while (hi - lo > 1u) {
+      const uint32_t mid = lo + (hi - lo) / 2u;
+      if (__fdiv_rn(__uint_as_float(mid), total) < qf) lo = mid; else hi = mid;
+    }
+    amax = __uint_as_float(lo);
+  }
   float acc = 0.f, t = __int_as_float(0x7fc00000);          // no share below the quantile: numpy raises IndexError; here nothing is flagged
   int done = 0;
   for (size_t c0 = 0; c0 < n && !done; c0 += TCH) {
@@ -179,9 +211,24 @@ __global__ void __launch_bounds__(32) k_label_threshold(int F, int vad, float qf
     for (int i = lane; i < m; i += 32) buf[i] = a[c0 + i];
     __syncwarp();
     if (lane == 0) {
-      for (int i = 0; i < m; ++i) {
+      int i = 0;
+      // groups of 8 with two 16-byte loads and ONE test: the running sums only grow, so a group whose last sum passes
+      // lies entirely below the quantile (same additions in the same order as the element-wise loop)
+      float4 u = make_float4(0.f, 0.f, 0.f, 0.f), v = u;
+      if (m >= 8) { u = *reinterpret_cast<const float4*>(buf); v = *reinterpret_cast<const float4*>(buf + 4); }
+      for (; i + 8 <= m; i += 8) {
+        const float4 cu = u, cv = v;
+        if (i + 16 <= m) { u = *reinterpret_cast<const float4*>(buf + i + 8); v = *reinterpret_cast<const float4*>(buf + i + 12); }   // next group, ahead of the adds
+        float a8 = __fadd_rn(acc, cu.x);
+        a8 = __fadd_rn(a8, cu.y); a8 = __fadd_rn(a8, cu.z); a8 = __fadd_rn(a8, cu.w);
+        a8 = __fadd_rn(a8, cv.x); a8 = __fadd_rn(a8, cv.y); a8 = __fadd_rn(a8, cv.z); a8 = __fadd_rn(a8, cv.w);
+        if (!(a8 <= amax)) break;
+        acc = a8;
+        t = cv.w;
+      }
+      for (; i < m; ++i) {                                  // the group at the crossing (or the chunk's tail), element by element
         acc = __fadd_rn(acc, buf[i]);
-        if (!(acc < safe) && !(__fdiv_rn(acc, total) < qf)) { done = 1; break; }
+        if (!(acc <= amax)) { done = 1; break; }
         t = buf[i];
       }
     }
@@ -232,7 +279,7 @@ int32_t launch_speech_labels(const gvn_batch* b, const float* S, int from_power,
   if ((rc = check_launch("k_label_keys"))) return rc;
   k_label_sort<<<b->B, LT, 0, st>>>(b->F, vad, b->n_frames, seg_off, keys, tmp);
   if ((rc = check_launch("k_label_sort"))) return rc;
-  k_label_threshold<<<b->B, 32, 0, st>>>(b->F, vad, qf, b->n_frames, seg_off, keys, thr);
+  k_label_threshold<<<b->B, 32, 0, st>>>(b->F, vad, qf, b->n_frames, seg_off, keys, tmp, thr);
   if ((rc = check_launch("k_label_threshold"))) return rc;
   const size_t total = (size_t)(vad ? 1 : b->F) * b->NP;
   int grid = (int)((total + 255) / 256);

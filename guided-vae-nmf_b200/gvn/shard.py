@@ -17,9 +17,27 @@ def shard_bounds(n, world, rank):
     return start, start + base + (1 if rank < extra else 0)
 
 
-def shard_list(items, world, rank):
-    a, b = shard_bounds(len(items), world, rank)
-    return items[a:b]
+def shard_list(items, world, rank, strided=False):
+    """Rank's share of a list.  Default: the reference's contiguous np.array_split shards.  ``strided``: for a list
+    that has been SORTED BY LENGTH -- dealt like cards in a snake (0 1 .. w-1, w-1 .. 1 0, ...), so that every rank
+    gets the same mix of long and short utterances: a contiguous shard of a sorted list would hand all the long ones
+    to one rank, and with utterances of 537-748 frames the slowest rank sets the time of the whole job."""
+    if not strided:
+        a, b = shard_bounds(len(items), world, rank)
+        return items[a:b]
+    out = []
+    for i, it in enumerate(items):
+        rnd, pos = divmod(i, world)
+        if (pos if rnd % 2 == 0 else world - 1 - pos) == rank:
+            out.append(it)
+    return out
+
+
+def length_sorted_shard(lengths, world, rank):
+    """Indices of rank's utterances: longest first, dealt in a snake (see shard_list).  Batches cut from this list
+    hold utterances of similar length."""
+    order = sorted(range(len(lengths)), key=lambda i: (-int(lengths[i]), i))
+    return shard_list(order, world, rank, strided=True)
 
 
 def gather_rows(rows, n_total, world=None, rank=None):

@@ -6,7 +6,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from gvn.shard import shard_bounds, shard_list, gather_rows
+from gvn.shard import shard_bounds, shard_list, gather_rows, length_sorted_shard
 
 
 def test_shard_bounds_match_array_split():
@@ -18,6 +18,23 @@ def test_shard_bounds_match_array_split():
                 a, b = shard_bounds(n, world, r)
                 assert list(range(a, b)) == list(ref[r])
     assert shard_list(list("abcde"), 2, 0) == ["a", "b", "c"] and shard_list(list("abcde"), 2, 1) == ["d", "e"]
+
+
+def test_length_sorted_snake_shards_are_balanced():
+    """C5 / real file lists: utterances of 537-748 frames.  Sorted by length and dealt in a snake, the ranks' frame totals
+    differ by less than one utterance; the reference's contiguous split of the same sorted list is off by tens of percent."""
+    lens = np.random.RandomState(5).randint(537, 749, size=1000)
+    for world in (2, 3, 8):
+        shards = [length_sorted_shard(lens, world, r) for r in range(world)]
+        assert sorted(i for s in shards for i in s) == list(range(1000))                 # a partition
+        assert max(len(s) for s in shards) - min(len(s) for s in shards) <= 1
+        tot = [int(lens[s].sum()) for s in shards]
+        assert max(tot) - min(tot) <= 748
+        for s in shards:                                                                  # longest first inside a shard
+            assert all(lens[a] >= lens[b] for a, b in zip(s, s[1:]))
+        order = sorted(range(1000), key=lambda i: -int(lens[i]))
+        contiguous = [int(lens[shard_list(order, world, r)].sum()) for r in range(world)]
+        assert max(contiguous) - min(contiguous) > 20 * (max(tot) - min(tot))
 
 
 def _worker(rank, world, port, n_total, q):
