@@ -29,7 +29,7 @@ int32_t check_launch(const char* what) {
 }
 
 // launchers implemented in the other translation units
-int32_t launch_estep_simt(const gvn_batch*, const void*, int, int, float, const gvn_noise*, const gvn_trace*, cudaStream_t);
+int32_t launch_estep_simt(const gvn_batch*, const void*, int, int, float, const gvn_noise*, const gvn_trace*, int, cudaStream_t);
 int32_t launch_estep_tc(const gvn_batch*, const void*, int, int, float, const gvn_noise*, const gvn_trace*, int, cudaStream_t);
 size_t mstep_workspace_bytes(const gvn_batch*);
 int32_t launch_mstep(const gvn_batch*, int, float*, void*, int, cudaStream_t);
@@ -106,9 +106,9 @@ int32_t gvn_estep(const gvn_batch* batch, const void* packed, int32_t burnin, in
   GVN_REQUIRE(burnin >= 0 && R >= 1 && R <= batch->R_cap, GVN_E_INVALID, "burnin=%d R=%d R_cap=%d", burnin, R, batch->R_cap);
   GVN_REQUIRE((noise->eps == nullptr) == (noise->u == nullptr), GVN_E_INVALID, "eps and u must both be given or both NULL");
   GVN_REQUIRE(var_RW > 0.f, GVN_E_INVALID, "var_RW=%g", (double)var_RW);
-  const int32_t prec = precision & ~GVN_PREC_XV_CURRENT;
+  const int32_t prec = precision & ~(GVN_PREC_XV_CURRENT | GVN_PREC_XV_BF16);
   if (prec == GVN_PREC_FP32)
-    return launch_estep_simt(batch, packed, burnin, R, var_RW, noise, trace, (cudaStream_t)stream);
+    return launch_estep_simt(batch, packed, burnin, R, var_RW, noise, trace, precision, (cudaStream_t)stream);
   if (prec == GVN_PREC_F16)
     return launch_estep_tc(batch, packed, burnin, R, var_RW, noise, trace, precision, (cudaStream_t)stream);
   return fail(GVN_E_INVALID, "unknown precision %d", precision);

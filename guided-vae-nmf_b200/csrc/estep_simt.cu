@@ -26,6 +26,7 @@ struct EstepArgs {
   float sd;                    // sqrt(var_RW) in fp32, as mcem.py:231,257
   const int32_t* frame_utt;
   const float* X2; const float* g; const float* Vb; const float* yproj;
+  int xv_bf16;
   float* Z; float* Vs; float* Vs_w;
   // decoder (fp32 section of the packed image)
   const float* w1zT; const float* w2T; const float* b2; const float* w3T; const float* b3; int FS;
@@ -175,6 +176,14 @@ __global__ void __launch_bounds__(NT, 2) k_estep_simt(EstepArgs p) {
               float4 vb = *reinterpret_cast<const float4*>(p.Vb + off);
               float4 x2 = *reinterpret_cast<const float4*>(p.X2 + off);
               float vbv[4] = {vb.x, vb.y, vb.z, vb.w}, x2v[4] = {x2.x, x2.y, x2.z, x2.w};
+              if (p.xv_bf16) {                               // GVN_PREC_XV_BF16: the tensor-core chain's view of the two constants
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const uint32_t w = pack_xv_word(x2v[i], vbv[i]);
+                  vbv[i] = __uint_as_float(w << 16);
+                  x2v[i] = __uint_as_float(w);
+                }
+              }
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 float vx = fmaf(gq[i], vs[i], vbv[i]);
@@ -303,13 +312,14 @@ size_t estep_simt_smem(int L) {
 }  // namespace
 
 int32_t launch_estep_simt(const gvn_batch* b, const void* packed, int burnin, int R,
-                          float var_RW, const gvn_noise* nz, const gvn_trace* tr, cudaStream_t stream) {
+                          float var_RW, const gvn_noise* nz, const gvn_trace* tr, int precision, cudaStream_t stream) {
   DecoderLayout d = decoder_layout(b->L, 0, b->F);
   const float* base = reinterpret_cast<const float*>(packed);
   EstepArgs a;
   a.F = b->F; a.L = b->L; a.NP = b->NP; a.burnin = burnin; a.R = R;
   a.sd = sqrtf(var_RW);
   a.frame_utt = b->frame_utt; a.X2 = b->X2; a.g = b->g; a.Vb = b->Vb; a.yproj = b->yproj;
+  a.xv_bf16 = (precision & GVN_PREC_XV_BF16) != 0;
   a.Z = b->Z; a.Vs = b->Vs; a.Vs_w = b->Vs_w;
   a.w1zT = base + d.w1zT; a.w2T = base + d.w2T; a.b2 = base + d.b2; a.w3T = base + d.w3T;
   a.b3 = base + d.b3; a.FS = d.FS;

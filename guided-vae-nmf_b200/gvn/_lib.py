@@ -14,7 +14,8 @@ GVN_MAX_K = 32
 GVN_MAX_L = 64
 PREC_FP32, PREC_F16 = 0, 2
 GVN_PREC_XV_CURRENT = 0x100
-PRECISIONS = {"fp32": PREC_FP32, "f16": PREC_F16}
+GVN_PREC_XV_BF16 = 0x200
+PRECISIONS = {"fp32": PREC_FP32, "f16": PREC_F16, "fp32_xvbf16": PREC_FP32 | GVN_PREC_XV_BF16}
 E_INVALID, E_UNSUPPORTED_SHAPE, E_CUDA, E_UNSUPPORTED_MODEL, E_BAD_WINDOW = -1, -2, -3, -4, -5
 
 _p = C.c_void_p

@@ -90,7 +90,11 @@ enum {
   /* flag, OR-ed into `precision`: batch->XV already matches (X2, Vb).  gvn_mstep rewrites XV next to
    * every Vb it writes, so inside the EM loop only the first gvn_estep has to pack it (the packing
    * pass reads X2 and Vb and writes XV: 100 MB per launch at 64 utterances). */
-  GVN_PREC_XV_CURRENT = 0x100
+  GVN_PREC_XV_CURRENT = 0x100,
+  /* flag for GVN_PREC_FP32 (diagnostic): the CUDA-core chain reads X2 and Vb through the bf16 rounding of XV, i.e.
+   * exactly the two constants the tensor-core chain sees, everything else in fp32 -- the A/B that isolates the
+   * effect of that rounding (tests/test_gpu_fullshape.py). */
+  GVN_PREC_XV_BF16 = 0x200
 };
 
 typedef struct gvn_batch {

@@ -1,6 +1,8 @@
 """M-step variant 1 (column tiles staged once in shared memory, pair-wise reciprocal/log) against
-variant 0 (the straightforward schedule that is pinned to the oracle by test_gpu_parity) on
-ragged batches at the benchmark shape, including tiles that lie entirely in padding."""
+variant 0 (the straightforward schedule: IEEE divisions, logf) on ragged batches at the benchmark shape,
+including tiles that lie entirely in padding and slots of multiplicity zero.  Both variants are compared
+with the ORACLE in tests/test_gpu_parity.py (golden shapes, variant 1) and tests/test_gpu_fullshape.py
+(benchmark shapes, variants 0 and 1); this file checks that they agree with each other on many more shapes."""
 import numpy as np
 import pytest
 import torch
