@@ -118,19 +118,23 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-// Watchdog of every barrier spin in this library: a wait that has not completed after GVN_WATCHDOG_NS of WALL time
-// (%globaltimer, sampled every 1024 failed polls) traps, so a protocol bug surfaces as a launch error instead of a
-// stuck device.  The bound is time, not a poll count -- the poll time of try_wait is implementation defined -- and it
-// is four orders of magnitude above the run time of any kernel here, profiler replay or sanitizer included.
+// Watchdog of the barrier spins, DEBUG BUILDS ONLY (make EXTRA=-DGVN_DEBUG_WATCHDOG): a wait that has not completed
+// after GVN_WATCHDOG_NS of wall time (%globaltimer, sampled every 1024 failed polls) traps, so that a protocol bug under
+// development surfaces as a launch error instead of a stuck device.  Release builds carry no watchdog at all: even on
+// its never-taken path the check sits inside every spin loop of the chain kernel, and it was measured at 8 % of the
+// chain's run time (0.546 -> 0.502 ms per 40-step chain at C2; the poll-count trap of round 1 cost 2 %) -- and a trap
+// that fires spuriously under a profiler or sanitizer leaves a sticky fault behind.
 #ifndef GVN_WATCHDOG_NS
 #define GVN_WATCHDOG_NS 20000000000ull
 #endif
 __device__ __forceinline__ void watchdog_poll(uint32_t spins, unsigned long long& t0) {
+#ifdef GVN_DEBUG_WATCHDOG
   if ((spins & 1023u) != 1023u) return;
   unsigned long long now;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
   if (t0 == 0ull) t0 = now;
   else if (now - t0 > GVN_WATCHDOG_NS) __trap();
+#endif
 }
 // Spin on try_wait (a hardware-suspended wait, not a busy poll).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {

@@ -215,15 +215,29 @@ class Enhancer:
             done.record(main)
             return out, done
 
+        # Packing (float64 -> float32 into pinned memory, a few tens of milliseconds per batch and far more when eight
+        # ranks share the host's cores) runs on a worker thread, so that it overlaps not only the GPU but also this
+        # thread's own work: queueing the ~1300 kernel launches of the batch before it.  torch copies and the ctypes
+        # calls into libgvn.so release the interpreter lock.
+        from concurrent.futures import ThreadPoolExecutor
+        pool = getattr(self, "_pack_pool", None)
+        if pool is None:
+            pool = self._pack_pool = ThreadPoolExecutor(1, thread_name_prefix="gvn-pack")
+
+        def upload_job(item, slot):
+            with torch.cuda.device(dev):
+                return start_upload(item, slot)
+
         it = iter(batches)
         nxt = next(it, None)
-        pending = start_upload(nxt, 0) if nxt is not None else None
+        pending = pool.submit(upload_job, nxt, 0) if nxt is not None else None
         in_flight = None                                    # (results, event) of the batch queued before the current one
         i = 0
         while pending is not None:
-            cur = launch(pending[0], pending[1], i)         # queued behind the batch in flight
-            nxt = next(it, None)                            # pack + copy the next batch while the GPU works
-            pending = start_upload(nxt, (i + 1) & 1) if nxt is not None else None
+            up, ev = pending.result()
+            nxt = next(it, None)                            # pack + copy the next batch while this thread queues the kernels of this one
+            pending = pool.submit(upload_job, nxt, (i + 1) & 1) if nxt is not None else None
+            cur = launch(up, ev, i)                         # queued behind the batch in flight
             if in_flight is not None:
                 in_flight[1].synchronize()
                 yield in_flight[0]
