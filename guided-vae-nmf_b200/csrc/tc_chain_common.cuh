@@ -63,6 +63,7 @@ __global__ void __launch_bounds__(256) k_pack_xv(size_t n4, const float4* __rest
 // parity wait for the two single-lane service warps: suspends in hardware between polls so that
 // their spinning does not take issue slots from the epilogue warps of the same scheduler
 __device__ __forceinline__ void mbar_wait_idle(uint64_t* bar, uint32_t parity) {
+#ifdef GVN_DEBUG_WATCHDOG
   uint32_t ok = 0;
   unsigned long long t0 = 0ull;
   for (uint32_t spins = 0; !ok; ++spins) {
@@ -73,6 +74,14 @@ __device__ __forceinline__ void mbar_wait_idle(uint64_t* bar, uint32_t parity) {
         : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(20000u) : "memory");
     if (!ok) watchdog_poll(spins | 1023u, t0);       // every failed poll already slept up to ~20 us (tc_common.cuh)
   }
+#else
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "GVN_WAITI_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "@!p bra GVN_WAITI_%=;\n\t}"
+      :: "r"(smem_u32(bar)), "r"(parity), "r"(20000u) : "memory");
+#endif
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
