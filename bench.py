@@ -17,10 +17,13 @@ dealt to the ranks and enhanced in batches: STRONG scaling (the list does not gr
 Ranks own disjoint utterance shards (no data-path collective); one NCCL all-gather of the per-utterance
 result rows closes each step.
 
-`value`  : utterances/s with the waveforms (and clean-speech references) already in HBM (CUDA events,
-           max over ranks).
-`e2e`    : the same through Enhancer.enhance_many with HOST buffers: pinned H2D of the waveforms and
-           references and D2H of both enhanced waveforms inside the timed region.
+`value`  : utterances/s with the inputs of the path already in HBM when the timed region starts: the waveforms,
+           the clean-speech / noise references of the quality metrics and the guide labels made from the clean
+           speech (CUDA events, max over ranks).
+`e2e`    : the same through Enhancer.enhance_many with HOST buffers, everything inside the timed region: packing,
+           pinned H2D of the waveforms and references, the oracle labels (clean-speech STFT, ranking, threshold: on
+           the device, queued on the copy stream behind the upload), the enhancement, D2H of both enhanced waveforms
+           and of the result rows.
 `roofline`: the dominant kernel (the fused decoder + Metropolis-Hastings chain, gvn_estep)
            against the measured bf16 tensor peak; `roofline_nmf`: the NMF M-step kernels
            against the measured HBM copy bandwidth.

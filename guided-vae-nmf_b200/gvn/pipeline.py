@@ -62,6 +62,21 @@ class Enhancer:
         with torch.cuda.device(self.device):
             self.dec = E.PackedDecoder(vae, self.device)
         self._batches = {}          # batch state in HBM is allocated once per shape and reused (stream-ordered)
+        import threading
+        self._batches_lock = threading.Lock()   # upload() may run on the packing thread of enhance_many
+
+    def _batch_for(self, geo):
+        """Device state for a batch of this geometry, allocated once per shape and reused (stream-ordered)."""
+        cfg = self.cfg
+        (R_E, _), (R_W, _) = cfg.chains()
+        key = (tuple(g[3] for g in geo), geo[0][0] // 2 + 1, cfg.nmf_rank, self.dec.L, max(R_E, R_W))
+        with self._batches_lock:
+            b = self._batches.get(key)
+            if b is None:
+                if len(self._batches) >= 4:
+                    self._batches.clear()
+                b = self._batches[key] = E.Batch(list(key[0]), key[1], key[2], key[3], key[4], self.device)
+        return b
 
     def upload(self, wavs, labels=None, refs=None, slot=0, clean=None):
         """Host -> device copy of one batch of inputs (pinned staging, async on the current stream): the
@@ -106,6 +121,18 @@ class Enhancer:
                     d.copy_(host, non_blocking=True)
                     out[name] = d
                     out["h2d_bytes"] += host.numel() * 4
+            # Oracle labels are made HERE, on the stream of the upload (in enhance_many: the copy stream, which idles while
+            # the compute stream runs the EM loop of the previous batch), from the clean speech that has just arrived:
+            # STFT, ranking and threshold per utterance on the device (gvn_speech_labels).  They travel on as up["y"].
+            if cfg.model == "M2" and y is None and self.label_source in ("oracle_ibm", "oracle_vad"):
+                src = out.get("clean", out.get("ref_s"))
+                if src is None:
+                    raise ValueError("label_source=%r needs the clean speech of the batch (clean= or refs=)" % self.label_source)
+                b = self._batch_for(geo)                    # only its frame index arrays are read
+                Sc = E.device_buffer("clean_Xc", (b.F, b.NP, 2), torch.float32, dev)
+                P2 = E.device_buffer("clean_X2", (b.F, b.NP), torch.float32, dev)
+                E.stft_to(b, src, T, T_stride, geo[0][0], geo[0][1], [g[2] for g in geo], Sc, P2)
+                out["y"] = E.speech_labels(b, Sc, self.label_source == "oracle_vad", self.quantile_fraction, self.quantile_weight)
         return out
 
     def prepare(self, wavs, labels=None, seed=0, rand=None, uploaded=None):
@@ -118,12 +145,7 @@ class Enhancer:
         nfft, hop = geo[0][0], geo[0][1]
         (R_E, _), (R_W, _) = cfg.chains()
         with torch.cuda.device(dev):
-            key = (tuple(g[3] for g in geo), nfft // 2 + 1, cfg.nmf_rank, self.dec.L, max(R_E, R_W))
-            b = self._batches.get(key)
-            if b is None:
-                if len(self._batches) >= 4:
-                    self._batches.clear()
-                b = self._batches[key] = E.Batch(list(key[0]), key[1], key[2], key[3], key[4], dev)
+            b = self._batch_for(geo)
             E.stft_into(b, up["wav"], up["T"], up["T_stride"], nfft, hop, [g[2] for g in geo])
             if rand is None:
                 E.init_nmf(b, cfg.eps, generator=torch.Generator(device=dev).manual_seed(int(seed)))
@@ -133,14 +155,6 @@ class Enhancer:
             if cfg.model == "M2":
                 if up["y"] is not None:
                     y = up["y"]
-                elif self.label_source in ("oracle_ibm", "oracle_vad"):
-                    clean = up.get("clean", up.get("ref_s"))
-                    if clean is None:
-                        raise ValueError("label_source=%r needs the clean speech of the batch (upload(..., clean=) or refs=)" % self.label_source)
-                    Sc = E.device_buffer("clean_Xc", (b.F, b.NP, 2), torch.float32, dev)
-                    P2 = E.device_buffer("clean_X2", (b.F, b.NP), torch.float32, dev)
-                    E.stft_to(b, clean, up["T"], up["T_stride"], nfft, hop, [g[2] for g in geo], Sc, P2)
-                    y = E.speech_labels(b, Sc, self.label_source == "oracle_vad", self.quantile_fraction, self.quantile_weight)
                 elif self.label_source == "timo":
                     b.y_soft, y = E.spp_mask(b)
                 else:
