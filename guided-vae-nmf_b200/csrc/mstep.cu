@@ -244,6 +244,9 @@ __global__ void k_cost_reduce(int B, int F, int R, int niter, int ntiles, const 
 }
 
 // ------------------------------------------------------------ Wiener (mcem.py:341-343, :175-176)
+// Threads walk the points in the column-tile order of Vs (tile, bin, frame-in-tile): the R slot reads of a warp -- the
+// bulk of the traffic, R x F x NP floats -- are 128 contiguous bytes each; Vb, X and the outputs ([F][NP] order) are
+// touched in whole 32- / 64-byte row segments.
 __global__ void __launch_bounds__(256) k_wiener(int F, int NP, int R, const int32_t* __restrict__ frame_utt,
                                                 const float* __restrict__ Vs, const float* __restrict__ Vs_w,
                                                 const float* __restrict__ Vb, const float* __restrict__ g,
@@ -251,15 +254,18 @@ __global__ void __launch_bounds__(256) k_wiener(int F, int NP, int R, const int3
                                                 float2* __restrict__ S_hat, float2* __restrict__ N_hat,
                                                 float* __restrict__ WFs, float* __restrict__ WFn) {
   const size_t total = (size_t)F * NP, slab = total;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int gn = (int)(i % NP), f = (int)(i / NP);
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int j = (int)(t % GVN_VS_TILE);
+    const size_t q = t / GVN_VS_TILE;
+    const int f = (int)(q % F), gn = (int)(q / F) * GVN_VS_TILE + j;
+    const size_t i = (size_t)f * NP + gn;
     float ws = 0.f, wn = 0.f;
     if (frame_utt[gn] >= 0) {
       const float gg = g[gn], vb = Vb[i];
       for (int r = 0; r < R; ++r) {
         const float w = Vs_w[(size_t)r * NP + gn];
         if (w == 0.f) continue;                                 // dead slot (rejected proposal)
-        const float sc = gg * Vs[tile_off(f, gn, F) + (size_t)r * slab];
+        const float sc = gg * Vs[t + (size_t)r * slab];
         const float wi = w * __frcp_rn(sc + vb);
         ws = fmaf(wi, sc, ws);
         wn = fmaf(wi, vb, wn);

@@ -267,10 +267,18 @@ def upload_waveforms(wavs, device, pinned=None, tag="wav"):
     T = [len(w) for w in wavs]
     T_stride = (max(T) + 3) // 4 * 4
     host = pinned if pinned is not None else pinned_buffer(tag, (B, T_stride))
-    for b, w in enumerate(wavs):
-        host[b, :T[b]].copy_(torch.from_numpy(np.ascontiguousarray(w)))      # f64 -> f32 conversion on the way
-        if T[b] < T_stride:
-            host[b, T[b]:] = 0
+    hn = host.numpy()
+    # numpy assignments (float64 -> float32 on the way): a torch copy_ per utterance costs ~1 ms of dispatch each -- 59 ms
+    # per 64-utterance batch on two threads against 5 ms -- which is what held the 8-rank end-to-end number back
+    if isinstance(wavs, np.ndarray) and wavs.ndim == 2:
+        hn[:, :wavs.shape[1]] = wavs
+        if wavs.shape[1] < T_stride:
+            hn[:, wavs.shape[1]:] = 0
+    else:
+        for b, w in enumerate(wavs):
+            hn[b, :T[b]] = w
+            if T[b] < T_stride:
+                hn[b, T[b]:] = 0
     dev = device_buffer(tag, (B, T_stride), torch.float32, device)
     dev.copy_(host, non_blocking=True)
     return dev, T, T_stride

@@ -114,9 +114,10 @@ class Enhancer:
                     host = E.pinned_buffer("%s%d" % (name, slot), (len(wavs), T_stride))
                     if isinstance(arr, np.ndarray) and arr.ndim == 2:            # equal lengths: one vectorised copy (f64 -> f32 on the way)
                         host[:, :arr.shape[1]].copy_(torch.from_numpy(np.ascontiguousarray(arr)))
-                    else:                                                        # ragged list
+                    else:                                                        # ragged list (numpy assignments: see upload_waveforms)
+                        hn = host.numpy()
                         for i, a in enumerate(arr):
-                            host[i, :len(a)].copy_(torch.from_numpy(np.ascontiguousarray(a)))
+                            hn[i, :len(a)] = a
                     d = E.device_buffer("%s%d" % (name, slot), host.shape, torch.float32, dev)
                     d.copy_(host, non_blocking=True)
                     out[name] = d
