@@ -960,6 +960,354 @@ __global__ void __launch_bounds__(GT, 2) k_cols_gen(GenArgs p) {
   }
 }
 
+// ------------------------------------------- streamed column sweep (any K <= 32, any R)
+// The generic sweep above loads every sample slot with scalar loads, three times per tile, and is bound by the latency
+// of those loads (C4: 0.58 ms per iteration, 9 % of the HBM peak).  This one moves the same bytes the way the W sweep
+// does: a producer warp streams the tile -- (R+1) planes, chunk after chunk of SFL frequency rows -- through a ring of
+// shared-memory stages with bulk async copies, ONCE PER PASS (the first pass from HBM, the other two from L2, where the
+// 180 KB a tile occupies are still resident), and the compute warps never touch global memory for the slots.  One row
+// per thread and chunk; the arithmetic, the reductions and the outputs are those of k_cols_gen.
+constexpr int SW_ = 12;                // compute warps (+ 1 producer warp: 13 warps, 128 registers)
+constexpr int SCT = SW_ * 32;
+constexpr int SFL = SCT / NB;          // 48 frequency rows per chunk
+constexpr int STT = SCT + 32;
+constexpr int SMAXST = 8;
+__host__ __device__ inline int stream_stage_floats(int R) { return (R + 1) * SFL * NB; }
+// a_s | s1_s ([F][NB] each) double as the scratch of the H product: SCT threads x 16 partial sums
+__host__ __device__ inline size_t stream_as_floats(int F) { const size_t a = (size_t)2 * F * NB, b = (size_t)SCT * 16; return a > b ? a : b; }
+__host__ __device__ inline size_t stream_fixed_floats(int F, int KS, int K, int R) {
+  return (size_t)F * KS + stream_as_floats(F) + (size_t)meta_stride(K, R) * NB + (size_t)K * NB + 32 + SW_ * 2 * NB + 32 + 2 * (2 * SMAXST + 2) + 16;
+}
+__device__ __forceinline__ void bar_stream() { asm volatile("bar.sync 1, %0;" ::"n"(SCT) : "memory"); }
+
+// Tensor maps of the sample slots and of X2 in column-tile order: Vs = [R][NP/8][F][8] f32 as a 4-D tensor (8, F, NP/8, R)
+// with box (8, SFL rows, 1 tile, R slots) -- ONE instruction fetches a chunk of all R planes (eleven separate bulk
+// copies of 1.5 KB cost the producer ~1 k cycles per chunk to issue) -- and X2t = [NP/8][F][8] as (8, F, NP/8) with box
+// (8, SFL, 1).  Rows beyond F read as zeros.
+struct StreamMaps { CUtensorMap vs, x2; };
+
+// RT > 0: the number of sample slots is a compile-time constant (10 in the M2 scripts and in BASELINE config 4): the slot
+// loops unroll, their offsets become immediates and the multiplicities of the thread's frame live in registers.
+template <int KMAX, int RT>
+__global__ void __launch_bounds__(STT, 1) k_cols_stream(const __grid_constant__ StreamMaps maps, GenArgs p, int nstage) {
+  extern __shared__ __align__(128) float ss[];
+  const int F = p.F, K = p.K, KS = p.KS, NP = p.NP, R = RT > 0 ? RT : p.R, MS = meta_stride(K, R), T8 = NP / NB;
+  const int SSt = stream_stage_floats(R);
+  constexpr int PSt = SFL * NB;   // stage, plane inside a stage (floats)
+  float* ring = ss;                                         // [nstage][(R+1)][SFL][NB]
+  float* W_s = ring + (size_t)nstage * SSt;                 // [F][KS]
+  float* a_s = W_s + (size_t)F * KS;                        // [F][NB]  X2 * s2 of the H pass, then Vb of the g pass
+  float* s1_s = a_s + (size_t)F * NB;                       // [F][NB]
+  float* meta = a_s + stream_as_floats(F);                  // records of the tile's 8 frames: H_old | g | multiplicities
+  float* Hn_s = meta + (size_t)MS * NB;                     // [K][NB]
+  float* cn_s = Hn_s + (size_t)K * NB;                      // [32]
+  float* red = cn_s + 32;                                   // [SW_][2][NB]
+  float* misc = red + SW_ * 2 * NB;                         // [32]
+  uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(misc + 32) + 7) & ~(uintptr_t)7);
+  uint64_t* full = bars;                                    // [nstage]
+  uint64_t* empty = bars + SMAXST;                          // [nstage]
+  uint64_t* mfull = bars + 2 * SMAXST;                      // column data of the tile landed
+  uint64_t* mempty = mfull + 1;                             // ... and may be overwritten
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int NCHK = (F + SFL - 1) / SFL;                     // chunks per pass
+  if (tid == 0) {
+    for (int s_ = 0; s_ < nstage; ++s_) { mbar_init(full + s_, 1); mbar_init(empty + s_, SW_); }
+    mbar_init(mfull, 1);
+    mbar_init(mempty, SW_);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const int t_first = p.ntiles - 1 - (int)blockIdx.x;
+
+  if (tid >= SCT) {
+    // ================= producer warp: lane = plane; one bulk copy per plane and chunk, three passes per tile =================
+    uint32_t q = 0, tiles = 0;                              // chunks issued so far, tiles started
+    for (int t = t_first; t >= 0; t -= gridDim.x) {
+      if (p.frame_utt[(size_t)t * NB] < 0) continue;        // tile entirely in padding: the compute warps skip it too
+      if (tiles > 0) mbar_wait(mempty, (tiles - 1) & 1);
+      if (lane == 0) {
+        mbar_expect_tx(mfull, (uint32_t)MS * NB * 4);
+        bulk_g2s(meta, p.Mt + (size_t)t * MS * NB, (uint32_t)MS * NB * 4, mfull);
+      }
+      ++tiles;
+      for (int pass = 0; pass < 3; ++pass) {
+        for (int c = 0; c < NCHK; ++c, ++q) {
+          const int st_ = q % nstage;
+          if (q >= (uint32_t)nstage) mbar_wait(empty + st_, ((q / nstage) - 1) & 1);
+          float* dst = ring + (size_t)st_ * SSt;
+          if (lane == 0) {
+            mbar_expect_tx(full + st_, (uint32_t)SSt * 4);                // whole boxes: rows beyond F arrive as zeros
+            tc::tma_load_4d(dst, &maps.vs, 0, c * SFL, t, 0, full + st_);
+            tc::tma_load_3d(dst + (size_t)R * PSt, &maps.x2, 0, c * SFL, t, full + st_);
+          }
+        }
+      }
+    }
+    return;
+  }
+
+  // ================= compute warps =================
+  const int n = tid & (NB - 1), fl = tid >> 3;              // column of the tile, frequency lane (row of a chunk)
+  int cur_b = -1, cur_fo = -1;
+  uint32_t q = 0, tiles = 0;
+  for (int t = t_first; t >= 0; t -= gridDim.x) {
+    const int b = p.frame_utt[(size_t)t * NB];
+    if (b < 0) { if (tid == 0) p.cost_part[t] = 0.f; continue; }
+    bar_stream();                                           // previous tile is done with the shared arrays
+    if (b != cur_b) {
+      cur_b = b;
+      cur_fo = p.frame_off[b];
+      const float* wsrc = p.Wun + (size_t)b * F * K;
+      for (int i = tid; i < F * K; i += SCT) { const int ff = i / K; W_s[ff * KS + (i - ff * K)] = __ldg(wsrc + i); }
+      if (KS > K) for (int i = tid; i < F * (KS - K); i += SCT) { const int ff = i / (KS - K); W_s[ff * KS + K + (i - ff * (KS - K))] = 0.f; }
+      bar_stream();
+      for (int k = warp; k < K; k += SW_) {                 // c_k = sum_f |W_fk|  (mcem.py:128)
+        float sum = 0.f;
+        for (int ff = lane; ff < F; ff += 32) sum += fabsf(W_s[ff * KS + k]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if (lane == 0) cn_s[k] = sum;
+      }
+    }
+    bar_stream();
+    if (t * NB == cur_fo) {                                 // the first tile of an utterance writes W / c (mcem.py:131)
+      float* wdst = p.W + (size_t)b * F * K;
+      for (int i = tid; i < F * K; i += SCT) { const int ff = i / K, k = i - ff * K; wdst[i] = W_s[ff * KS + k] / cn_s[k]; }
+    }
+    mbar_wait(mfull, tiles & 1);
+    ++tiles;
+    const bool valid = p.frame_utt[(size_t)t * NB + n] >= 0;
+    const float* mrec = meta + n * MS;                      // record of this thread's frame
+    const float gg = mrec[K];
+    const float* wsm = mrec + K + 1;
+    float wr[RT > 0 ? RT : 1];
+    if (RT > 0) {
+#pragma unroll
+      for (int r = 0; r < RT; ++r) wr[RT > 0 ? r : 0] = wsm[r];
+    }
+    auto wgt = [&](int r) -> float { return RT > 0 ? wr[RT > 0 ? r : 0] : wsm[r]; };
+    float hk[KMAX];
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) hk[k] = (k < K) ? mrec[k] : 0.f;
+    auto dot_w = [&](const float* wrow, const float (&h)[KMAX]) -> float {
+      f2 acc = F2(0.f, 0.f);
+#pragma unroll
+      for (int k4 = 0; k4 < KMAX; k4 += 4) {
+        const float4 t4 = *reinterpret_cast<const float4*>(wrow + k4);
+        acc = fma2(F2(t4.x, t4.y), F2(h[k4], h[k4 + 1]), fma2(F2(t4.z, t4.w), F2(h[k4 + 2], h[k4 + 3]), acc));
+      }
+      return acc.x + acc.y;
+    };
+    // next chunk of the stream: waits for its stage; returns the stage's base and this thread's row (or -1 past the spectrum)
+    auto next_chunk = [&](int c, int& f) -> const float* {
+      const int st_ = q % nstage;
+      mbar_wait(full + st_, (q / nstage) & 1);
+      f = c * SFL + fl;
+      if (f >= F) f = -1;
+      return ring + (size_t)st_ * SSt + fl * NB + n;
+    };
+    auto done_chunk = [&]() {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty + (q % nstage));
+      ++q;
+    };
+
+    // ---------------- pass A: s1, s2 with Vb = Wun @ H_old (mcem.py:113-121)
+    for (int c = 0; c < NCHK; ++c) {
+      int f;
+      const float* vs = next_chunk(c, f);
+      if (f >= 0) {
+        const float vb = dot_w(W_s + f * KS, hk);
+        float s1 = 0.f, s2 = 0.f;
+        if (RT > 0) {
+#pragma unroll
+          for (int r = 0; r + 1 < RT; r += 2) pair_acc(gg, vb, vs[r * PSt], vs[(r + 1) * PSt], wgt(r), wgt(r + 1), s1, s2);
+          if (RT & 1) single_acc(gg, vb, vs[(RT - 1) * PSt], wgt(RT - 1), s1, s2);
+        } else {
+          int r = 0;
+          for (; r + 1 < R; r += 2) pair_acc(gg, vb, vs[r * PSt], vs[(r + 1) * PSt], wgt(r), wgt(r + 1), s1, s2);
+          if (r < R) single_acc(gg, vb, vs[r * PSt], wgt(r), s1, s2);
+        }
+        a_s[f * NB + n] = vs[R * PSt] * s2;
+        s1_s[f * NB + n] = s1;
+      }
+      done_chunk();
+    }
+    bar_stream();
+    // H update  H <- H * sqrt( (W^T (X2 s2)) / (W^T s1) ): thread = (slice of the frequency rows, group of four dictionary
+    // columns, frame) with eight accumulators, then the slices are summed through the (now free) a_s array
+    {
+      // thread = (slice of the frequency rows, group of four dictionary columns, PAIR of frames): sixteen accumulators as
+      // eight packed pairs per 16-byte load of W and two 8-byte loads of a / s1
+      const int KQ = (K + 3) / 4, combos = KQ * (NB / 2), nfs = SCT / combos;
+      const int fs = tid / combos, rem = tid - fs * combos, kq = rem / (NB / 2), np2 = (rem % (NB / 2)) * 2;
+      f2 nu[4], de[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) nu[i] = de[i] = F2(0.f, 0.f);
+      if (fs < nfs) {
+        const float* wp = W_s + (size_t)fs * KS + 4 * kq;
+        const float* ap = a_s + fs * NB + np2;
+        const float* sp = s1_s + fs * NB + np2;
+        for (int f = fs; f < F; f += nfs, wp += (size_t)nfs * KS, ap += nfs * NB, sp += nfs * NB) {
+          const float4 w4 = *reinterpret_cast<const float4*>(wp);                          // columns beyond K are zero (KS >= KMAX)
+          const f2 av = *reinterpret_cast<const float2*>(ap), sv = *reinterpret_cast<const float2*>(sp);
+          nu[0] = fma2(F2(w4.x, w4.x), av, nu[0]); de[0] = fma2(F2(w4.x, w4.x), sv, de[0]);
+          nu[1] = fma2(F2(w4.y, w4.y), av, nu[1]); de[1] = fma2(F2(w4.y, w4.y), sv, de[1]);
+          nu[2] = fma2(F2(w4.z, w4.z), av, nu[2]); de[2] = fma2(F2(w4.z, w4.z), sv, de[2]);
+          nu[3] = fma2(F2(w4.w, w4.w), av, nu[3]); de[3] = fma2(F2(w4.w, w4.w), sv, de[3]);
+        }
+      }
+      bar_stream();                                         // everybody has read a_s / s1_s
+      float* part = a_s;                                    // [nfs][4 KQ][NB][2]
+      if (fs < nfs) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float* d = part + (((size_t)fs * 4 * KQ + 4 * kq + i) * NB + np2) * 2;
+          *reinterpret_cast<float4*>(d) = make_float4(nu[i].x, de[i].x, nu[i].y, de[i].y);
+        }
+      }
+      bar_stream();
+      if (tid < K * NB) {
+        const int k = tid / NB;
+        float sn = 0.f, sd_ = 0.f;
+        for (int qq = 0; qq < nfs; ++qq) { const float* d = part + (((size_t)qq * 4 * KQ + k) * NB + n) * 2; sn += d[0]; sd_ += d[1]; }
+        Hn_s[tid] = meta[n * MS + k] * sqrtf(sn / sd_);
+      }
+    }
+    bar_stream();
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) hk[k] = (k < K) ? Hn_s[k * NB + n] : 0.f;      // hk is H_new from here on
+
+    // ---------------- pass B: Vb = Wun @ H_new (mcem.py:124), g update (:138-142)
+    float ng = 0.f, dg = 0.f;
+    for (int c = 0; c < NCHK; ++c) {
+      int f;
+      const float* vs = next_chunk(c, f);
+      if (f >= 0) {
+        const float vb = dot_w(W_s + f * KS, hk);
+        const float x2 = vs[R * PSt];
+        if (valid) {
+          p.Vb[(size_t)f * NP + (size_t)t * NB + n] = vb;
+          if (p.XV != nullptr) p.XV[(size_t)f * NP + (size_t)t * NB + n] = pack_xv_word(x2, vb);
+        }
+        a_s[f * NB + n] = vb;                               // kept for the cost pass
+        float t1 = 0.f, t2 = 0.f;
+        auto pairB = [&](int r) {
+          const float va = vs[r * PSt], vc = vs[(r + 1) * PSt];
+          const float a = fmaf(gg, va, vb), cc = fmaf(gg, vc, vb);
+          const float ip = rcp_fast(a * cc);
+          const float ia = cc * ip, ic = a * ip;
+          const float ua = wgt(r) * va * ia, uc = wgt(r + 1) * vc * ic;
+          t1 += ua + uc;
+          t2 = fmaf(ua, ia, fmaf(uc, ic, t2));
+        };
+        auto singleB = [&](int r) {
+          const float va = vs[r * PSt];
+          const float ia = rcp_fast(fmaf(gg, va, vb)), ua = wgt(r) * va * ia;
+          t1 += ua;
+          t2 = fmaf(ua, ia, t2);
+        };
+        if (RT > 0) {
+#pragma unroll
+          for (int r = 0; r + 1 < RT; r += 2) pairB(r);
+          if (RT & 1) singleB(RT - 1);
+        } else {
+          int r = 0;
+          for (; r + 1 < R; r += 2) pairB(r);
+          if (r < R) singleB(r);
+        }
+        ng = fmaf(x2, t2, ng);
+        dg += t1;
+      }
+      done_chunk();
+    }
+    ng += __shfl_xor_sync(0xffffffffu, ng, 8);
+    ng += __shfl_xor_sync(0xffffffffu, ng, 16);
+    dg += __shfl_xor_sync(0xffffffffu, dg, 8);
+    dg += __shfl_xor_sync(0xffffffffu, dg, 16);
+    if (lane < NB) { red[(warp * 2) * NB + lane] = ng; red[(warp * 2 + 1) * NB + lane] = dg; }
+    bar_stream();
+    float sn = 0.f, sd = 0.f;
+#pragma unroll
+    for (int w8 = 0; w8 < SW_; ++w8) { sn += red[(w8 * 2) * NB + n]; sd += red[(w8 * 2 + 1) * NB + n]; }
+    const float gnew = gg * sqrtf(sn / sd);
+    if (tid < NB && valid) p.g[(size_t)t * NB + n] = gnew;
+    if (tid < K * NB && valid) p.H[(size_t)(tid >> 3) * NP + (size_t)t * NB + n] = Hn_s[tid] * cn_s[tid >> 3];   // mcem.py:133
+
+    // ---------------- pass C: cost with the new g (mcem.py:151-152, :68-70)
+    float cl = 0.f, cr = 0.f;
+    for (int c = 0; c < NCHK; ++c) {
+      int f;
+      const float* vs = next_chunk(c, f);
+      if (f >= 0) {
+        const float vb = a_s[f * NB + n];
+        float sl = 0.f, sr = 0.f;
+        auto pairC = [&](int r) {
+          const float a = fmaf(gnew, vs[r * PSt], vb), cc = fmaf(gnew, vs[(r + 1) * PSt], vb);
+          const float wa = wgt(r), wc = wgt(r + 1);
+          sl = fmaf(wa, lg2_fast(a), fmaf(wc, lg2_fast(cc), sl));
+          sr = fmaf(fmaf(wa, cc, wc * a), rcp_fast(a * cc), sr);
+        };
+        auto singleC = [&](int r) {
+          const float a = fmaf(gnew, vs[r * PSt], vb), wa = wgt(r);
+          sl = fmaf(wa, lg2_fast(a), sl);
+          sr = fmaf(wa, rcp_fast(a), sr);
+        };
+        if (RT > 0) {
+#pragma unroll
+          for (int r = 0; r + 1 < RT; r += 2) pairC(r);
+          if (RT & 1) singleC(RT - 1);
+        } else {
+          int r = 0;
+          for (; r + 1 < R; r += 2) pairC(r);
+          if (r < R) singleC(r);
+        }
+        cl += sl;
+        cr = fmaf(vs[R * PSt], sr, cr);
+      }
+      done_chunk();
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(mempty);                     // the column data of this tile (wts) is not read any more
+    float cs = valid ? fmaf(cl, 0.6931471805599453f, cr) : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cs += __shfl_xor_sync(0xffffffffu, cs, o);
+    if (lane == 0) misc[warp] = cs;
+    bar_stream();
+    if (tid == 0) {
+      float sum = 0.f;
+      for (int w8 = 0; w8 < SW_; ++w8) sum += misc[w8];
+      p.cost_part[t] = sum;
+    }
+  }
+}
+
+template <int KMAX, int RT>
+int32_t launch_cols_stream(const GenArgs& a, int nstage, size_t smem, int grid, cudaStream_t st) {
+  static size_t smem_tab[GVN_MAX_DEVICES] = {0};
+  size_t& smem_set = *per_device_slot(smem_tab);
+  if (smem_set != smem) {
+    cudaError_t e = cudaFuncSetAttribute(k_cols_stream<KMAX, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(GVN_E_CUDA, "k_cols_stream smem attr (%zu B): %s", smem, cudaGetErrorString(e));
+    smem_set = smem;
+  }
+  static thread_local StreamMaps maps;                  // encoded once per (pointers, shape)
+  static thread_local const void* m_vs = nullptr; static thread_local const void* m_x2 = nullptr;
+  static thread_local int m_F = 0, m_NP = 0, m_R = 0;
+  if (m_vs != a.Vs || m_x2 != a.X2t || m_F != a.F || m_NP != a.NP || m_R != a.R) {
+    const uint64_t T8 = (uint64_t)a.NP / NB;
+    const uint64_t d4[4] = {(uint64_t)NB, (uint64_t)a.F, T8, (uint64_t)a.R};
+    const uint64_t s4[3] = {(uint64_t)NB * 4, (uint64_t)a.F * NB * 4, T8 * a.F * NB * 4};
+    const uint32_t b4[4] = {(uint32_t)NB, (uint32_t)SFL, 1u, (uint32_t)a.R};
+    int rc = tc::encode_f32_map(&maps.vs, a.Vs, 4, d4, s4, b4);
+    if (rc == 0) rc = tc::encode_f32_map(&maps.x2, a.X2t, 3, d4, s4, b4);
+    if (rc != 0) return fail(GVN_E_CUDA, "cuTensorMapEncodeTiled failed with %d (column sweep)", rc);
+    m_vs = a.Vs; m_x2 = a.X2t; m_F = a.F; m_NP = a.NP; m_R = a.R;
+  }
+  k_cols_stream<KMAX, RT><<<grid, STT, smem, st>>>(maps, a, nstage);
+  return check_launch("k_cols_stream");
+}
+
 template <int KMAX>
 int32_t launch_cols_gen(const GenArgs& a, size_t smem, int grid, cudaStream_t st) {
   static size_t smem_tab[GVN_MAX_DEVICES] = {0};
@@ -1104,6 +1452,19 @@ int32_t launch_mstep_v1(const gvn_batch* b, int R, float* cost_part, float* Mt, 
   a.F = b->F; a.K = b->K; a.KS = ks_gen(b->K); a.NP = b->NP; a.R = R; a.ntiles = ntiles;
   a.frame_utt = b->frame_utt; a.frame_off = b->frame_off; a.X2t = b->X2t; a.Vs = b->Vs; a.Mt = Mt;
   a.Vb = b->Vb; a.g = b->g; a.H = b->H; a.Wun = b->Wun; a.W = b->W; a.cost_part = cost_part; a.XV = b->XV;
+  static int force_scalar = -1;                         // GVN_MSTEP_GEN=2: the scalar-load generic sweep instead of the streamed one (experiments)
+  if (force_scalar < 0) { const char* e = getenv("GVN_MSTEP_GEN"); force_scalar = e ? atoi(e) == 2 : 0; }
+  {
+    const size_t fixed = stream_fixed_floats(b->F, a.KS, b->K, R) * 4, stage = (size_t)stream_stage_floats(R) * 4;
+    int nstage = fixed < 227 * 1024 ? (int)((227 * 1024 - fixed) / stage) : 0;
+    if (nstage > SMAXST) nstage = SMAXST;
+    if (nstage >= 3 && !force_scalar) {
+      const int grid_s = ntiles < sms ? ntiles : sms;
+      const size_t smem_s = fixed + (size_t)nstage * stage;
+      if (R == 10) return b->K <= 16 ? launch_cols_stream<16, 10>(a, nstage, smem_s, grid_s, st) : launch_cols_stream<32, 10>(a, nstage, smem_s, grid_s, st);
+      return b->K <= 16 ? launch_cols_stream<16, 0>(a, nstage, smem_s, grid_s, st) : launch_cols_stream<32, 0>(a, nstage, smem_s, grid_s, st);
+    }
+  }
   const size_t smem = gen_smem_floats(b->F, a.KS, b->K, R) * 4;
   const int per_sm = smem <= 110 * 1024 ? 2 : 1;
   const int grid = ntiles < sms * per_sm ? ntiles : sms * per_sm;
