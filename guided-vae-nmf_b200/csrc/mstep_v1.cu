@@ -1119,9 +1119,17 @@ __global__ void __launch_bounds__(STT, 1) k_cols_stream(const __grid_constant__ 
       if (f >= 0) {
         const float vb = dot_w(W_s + f * KS, hk);
         float s1 = 0.f, s2 = 0.f;
-        if (RT > 0) {
+        if (RT > 0) {                                       // four slots at a time in packed f32x2 arithmetic (as k_cols_v1)
+          f2 s1v = F2(0.f, 0.f), s2v = F2(0.f, 0.f);
+          const f2 g2 = F2(gg, gg), vb2 = F2(vb, vb);
 #pragma unroll
-          for (int r = 0; r + 1 < RT; r += 2) pair_acc(gg, vb, vs[r * PSt], vs[(r + 1) * PSt], wgt(r), wgt(r + 1), s1, s2);
+          for (int r = 0; r + 3 < RT; r += 4)
+            quad_acc(g2, vb2, F2(vs[r * PSt], vs[(r + 1) * PSt]), F2(vs[(r + 2) * PSt], vs[(r + 3) * PSt]), F2(wgt(r), wgt(r + 1)),
+                     F2(wgt(r + 2), wgt(r + 3)), s1v, s2v);
+          s1 = s1v.x + s1v.y;
+          s2 = s2v.x + s2v.y;
+          constexpr int R4 = RT / 4 * 4;
+          if (RT - R4 >= 2) pair_acc(gg, vb, vs[R4 * PSt], vs[(R4 + 1) * PSt], wgt(R4), wgt(R4 + 1), s1, s2);
           if (RT & 1) single_acc(gg, vb, vs[(RT - 1) * PSt], wgt(RT - 1), s1, s2);
         } else {
           int r = 0;
@@ -1208,8 +1216,16 @@ __global__ void __launch_bounds__(STT, 1) k_cols_stream(const __grid_constant__ 
           t2 = fmaf(ua, ia, t2);
         };
         if (RT > 0) {
+          f2 t1v = F2(0.f, 0.f), t2v = F2(0.f, 0.f);
+          const f2 g2 = F2(gg, gg), vb2 = F2(vb, vb);
 #pragma unroll
-          for (int r = 0; r + 1 < RT; r += 2) pairB(r);
+          for (int r = 0; r + 3 < RT; r += 4)
+            quad_accB(g2, vb2, F2(vs[r * PSt], vs[(r + 1) * PSt]), F2(vs[(r + 2) * PSt], vs[(r + 3) * PSt]), F2(wgt(r), wgt(r + 1)),
+                      F2(wgt(r + 2), wgt(r + 3)), t1v, t2v);
+          t1 = t1v.x + t1v.y;
+          t2 = t2v.x + t2v.y;
+          constexpr int R4 = RT / 4 * 4;
+          if (RT - R4 >= 2) pairB(R4);
           if (RT & 1) singleB(RT - 1);
         } else {
           int r = 0;
@@ -1254,8 +1270,16 @@ __global__ void __launch_bounds__(STT, 1) k_cols_stream(const __grid_constant__ 
           sr = fmaf(wa, rcp_fast(a), sr);
         };
         if (RT > 0) {
+          f2 slv = F2(0.f, 0.f), srv = F2(0.f, 0.f);
+          const f2 g2 = F2(gnew, gnew), vb2 = F2(vb, vb);
 #pragma unroll
-          for (int r = 0; r + 1 < RT; r += 2) pairC(r);
+          for (int r = 0; r + 3 < RT; r += 4)
+            quad_accC(g2, vb2, F2(vs[r * PSt], vs[(r + 1) * PSt]), F2(vs[(r + 2) * PSt], vs[(r + 3) * PSt]), F2(wgt(r), wgt(r + 1)),
+                      F2(wgt(r + 2), wgt(r + 3)), slv, srv);
+          sl = slv.x + slv.y;
+          sr = srv.x + srv.y;
+          constexpr int R4 = RT / 4 * 4;
+          if (RT - R4 >= 2) pairC(R4);
           if (RT & 1) singleC(RT - 1);
         } else {
           int r = 0;
