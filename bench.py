@@ -61,7 +61,7 @@ CONFIGS = {
     "C4": dict(model="M1", y_dim=0, labels=None, batch=8, T=480000, K=32, mcem=dict(burnin_E_step=10),
                text="C4: M1 VAE, {B} utt/GPU x 30 s @16 kHz (N=1876), F=513, K={K}, z_dim=16, 10 MH samples per frame (NMF stress)"),
     "C5": dict(model="M2", y_dim=513, labels="oracle_ibm", batch=64, T=None, K=10, mcem={},
-               text="C5: M2 guided VAE, oracle IBM labels, a fixed list of {U} ragged utterances (537-748 frames), length-sorted, batches of {B}, F=513, K={K}, z_dim=16"),
+               text="C5: M2 guided VAE, oracle IBM labels, a fixed list of {U} ragged utterances (537-748 frames), length-sorted, {BT}, F=513, K={K}, z_dim=16"),
 }
 
 
@@ -73,12 +73,15 @@ def product_paths():
 
 def workload(args):
     c = CONFIGS[args.config]
-    d = dict(workload=c["text"].format(B=args.batch, K=args.rank_k, U=args.utterances) + ", niter=%d" % args.niter,
+    bt = "batches of %d" % args.batch if args.waves <= 0 else "batches sized to %d full waves of 128-frame chain tiles" % args.waves
+    d = dict(workload=c["text"].format(B=args.batch, K=args.rank_k, U=args.utterances, BT=bt) + ", niter=%d" % args.niter,
              utterances_per_gpu=args.batch, niter=args.niter, precision=args.precision,
              l2="working set (Vs alone > 300 MB/GPU) exceeds the 126 MB L2; no explicit flush",
              parallelism="utterance shards, 1 process/GPU")
     if args.config == "C5":
         d["utterances_total"] = args.utterances
+        if args.waves > 0:
+            del d["utterances_per_gpu"]                     # the batch size follows from the lengths (wave_batches)
     return d
 
 
@@ -394,6 +397,9 @@ def main():
     ap.add_argument("--config", default="C2", choices=sorted(CONFIGS))
     ap.add_argument("--batch", type=int, default=None, help="utterances per GPU and step (default: the config's)")
     ap.add_argument("--utterances", type=int, default=1024, help="C5: length of the fixed utterance list")
+    ap.add_argument("--waves", type=int, default=2,
+                    help="C5: a batch takes as many utterances as fit this many full waves of 128-frame chain tiles "
+                         "(one tile per SM); 0 = fixed batches of --batch utterances")
     ap.add_argument("--niter", type=int, default=100)
     ap.add_argument("--rank-k", type=int, default=None)
     ap.add_argument("--precision", default=os.environ.get("GVN_PRECISION", "f16"),
@@ -419,7 +425,7 @@ def main():
     import torch
     import torch.distributed as dist
     from gvn.pipeline import McemConfig, Enhancer
-    from gvn.shard import length_sorted_shard
+    from gvn.shard import length_sorted_shard, wave_batches
     from gvn.synth import synth_batch, synth_utterance
     from gvn import engine as E
 
@@ -453,7 +459,11 @@ def main():
             if key not in pool:
                 pool[key] = synth_utterance(i % 64, seed=0, T=T)
             return pool[key]
-        groups = [mine[k:k + B] for k in range(0, len(mine), B)]
+        if args.waves > 0:                                  # batches sized to whole waves of chain tiles (gvn.shard.wave_batches)
+            sms = torch.cuda.get_device_properties(dev).multi_processor_count
+            groups = [mine[a:b_] for a, b_ in wave_batches([lens[i] for i in mine], sms, args.waves, max_batch=4 * B)]
+        else:
+            groups = [mine[k:k + B] for k in range(0, len(mine), B)]
         batches = []
         for g in groups:
             xs, ss, ns = zip(*[utt(i) for i in g])

@@ -117,7 +117,9 @@ def dense(W, b, in0, in1, act, NP, mean=None, std=None, eps=0.0):
 class Batch:
     """Device state of B utterances (layout documented in include/gvn.h)."""
 
-    def __init__(self, n_frames, F, K, L, R_cap, device, with_complex=True):
+    def __init__(self, n_frames, F, K, L, R_cap, device, with_complex=True, index_only=False):
+        """``index_only``: only the frame index arrays (frame_off, n_frames, frame_utt) are allocated -- enough for the
+        entry points that take their arrays as separate arguments (gvn_stft_power through stft_to, gvn_speech_labels)."""
         device = _require_cuda(device)
         self.device = device
         n_frames = [int(n) for n in n_frames]
@@ -133,10 +135,24 @@ class Batch:
         utt = np.full(self.NP, -1, np.int32)
         for b, n in enumerate(n_frames):
             utt[off[b]:off[b] + n] = b
-        i32 = dict(dtype=torch.int32, device=device)
-        self.frame_off = torch.tensor(off, **i32)
-        self.n_frames = torch.tensor(n_frames, **i32)
-        self.frame_utt = torch.from_numpy(utt).to(device)
+        # One pinned block, one asynchronous copy: a pageable host-to-device copy (torch.tensor(list, device=...)) is
+        # ordered by the runtime behind ALL work queued on the stream and blocks the host until then -- with a batch in
+        # flight that is the whole enhancement of the previous batch (see const_i32).
+        nb = len(n_frames)
+        seg = (nb + 1 + 63) // 64 * 64                      # every array starts on a 256-byte boundary
+        host = torch.zeros(2 * seg + self.NP, dtype=torch.int32).pin_memory()
+        hn = host.numpy()
+        hn[:nb + 1], hn[seg:seg + nb], hn[2 * seg:] = off, n_frames, utt
+        idx = host.to(device, non_blocking=True)
+        self.frame_off, self.n_frames, self.frame_utt = idx[:nb + 1], idx[seg:seg + nb], idx[2 * seg:]
+        self._alloc_stream = torch.cuda.current_stream(device)
+        self._streams = {self._alloc_stream}
+        self._struct = None
+        self.y = None
+        if index_only:
+            for name in ("X2", "Xc", "W", "Wun", "H", "g", "Vb", "Z", "Vs", "X2t", "Vs_w", "XV", "yproj"):
+                setattr(self, name, None)
+            return
         f32 = dict(dtype=torch.float32, device=device)
         NP = self.NP
         self.X2 = torch.ones(F, NP, **f32)
@@ -153,8 +169,18 @@ class Batch:
         self.Vs_w = torch.zeros(R_cap, NP, **f32)
         self.XV = torch.empty(F, NP, dtype=torch.int32, device=device)
         self.yproj = torch.zeros(GVN_HIDDEN, NP, **f32)
-        self.y = None
-        self._struct = None
+
+    def use_on(self, stream):
+        """Declares that kernels reading or writing this batch are being queued on `stream`.  The tensors belong to the
+        caching allocator's pool of the stream they were allocated on; without this, dropping the batch while another
+        stream still works on it hands its memory to the next allocation on the first stream (an upload thread building
+        the next batch, say) -- which overwrites index arrays a running kernel is about to read."""
+        if stream in self._streams:
+            return
+        self._streams.add(stream)
+        for t in vars(self).values():
+            if isinstance(t, torch.Tensor) and t.is_cuda:
+                t.record_stream(stream)
 
     def struct(self):
         if self._struct is not None:            # pointers and dims never change after construction
@@ -250,13 +276,22 @@ def const_i32(values, device):
     """Small read-only int32 vector on the device (lengths, paddings), created once per distinct content.
     A fresh ``torch.tensor(list, device=...)`` is a pageable host-to-device copy, which the CUDA runtime
     orders behind ALL work already queued on the stream: placed after the EM loop it stalls the host for
-    the whole enhancement and nothing can be prepared for the next batch meanwhile."""
+    the whole enhancement and nothing can be prepared for the next batch meanwhile -- so the copy goes through
+    pinned memory, asynchronously.  The vectors are shared between streams (an upload stream makes them, the
+    compute stream reads them again): every use is recorded, so that dropping old entries cannot hand their
+    memory to another stream's allocation while a queued kernel still reads it."""
     key = (tuple(int(v) for v in values), str(device))
     t = _CONST_I32.get(key)
     if t is None:
-        if len(_CONST_I32) >= 256:
-            _CONST_I32.clear()
-        t = _CONST_I32[key] = torch.tensor(list(key[0]), dtype=torch.int32, device=device)
+        while len(_CONST_I32) >= 256:
+            _CONST_I32.pop(next(iter(_CONST_I32)))
+        host = torch.tensor(list(key[0]), dtype=torch.int32).pin_memory()
+        t = _CONST_I32[key] = host.to(device, non_blocking=True)
+        t._gvn_streams = set()
+    st = torch.cuda.current_stream(t.device)
+    if st not in t._gvn_streams:
+        t._gvn_streams.add(st)
+        t.record_stream(st)
     return t
 
 

@@ -71,11 +71,13 @@ class Enhancer:
         (R_E, _), (R_W, _) = cfg.chains()
         key = (tuple(g[3] for g in geo), geo[0][0] // 2 + 1, cfg.nmf_rank, self.dec.L, max(R_E, R_W))
         with self._batches_lock:
-            b = self._batches.get(key)
+            b = self._batches.pop(key, None)
             if b is None:
-                if len(self._batches) >= 4:
-                    self._batches.clear()
-                b = self._batches[key] = E.Batch(list(key[0]), key[1], key[2], key[3], key[4], self.device)
+                while len(self._batches) >= 4:              # every batch of a real file list has its own geometry
+                    self._batches.pop(next(iter(self._batches)))     # the least recently used one goes
+                b = E.Batch(list(key[0]), key[1], key[2], key[3], key[4], self.device)
+            self._batches[key] = b                          # most recently used last
+        b.use_on(torch.cuda.current_stream(self.device))    # memory is reclaimed in the order of EVERY stream that used it
         return b
 
     def upload(self, wavs, labels=None, refs=None, slot=0, clean=None):
@@ -129,7 +131,9 @@ class Enhancer:
                 src = out.get("clean", out.get("ref_s"))
                 if src is None:
                     raise ValueError("label_source=%r needs the clean speech of the batch (clean= or refs=)" % self.label_source)
-                b = self._batch_for(geo)                    # only its frame index arrays are read
+                # only the frame index arrays are read: a batch of its own, allocated, used and dropped on this stream
+                # (the full batch state is allocated by prepare() on the compute stream)
+                b = E.Batch([g[3] for g in geo], geo[0][0] // 2 + 1, 1, 1, 1, dev, index_only=True)
                 Sc = E.device_buffer("clean_Xc", (b.F, b.NP, 2), torch.float32, dev)
                 P2 = E.device_buffer("clean_X2", (b.F, b.NP), torch.float32, dev)
                 E.stft_to(b, src, T, T_stride, geo[0][0], geo[0][1], [g[2] for g in geo], Sc, P2)

@@ -40,6 +40,31 @@ def length_sorted_shard(lengths, world, rank):
     return shard_list(order, world, rank, strided=True)
 
 
+def chain_tiles(n_frames, align=32, tile=128):
+    """Number of 128-frame tiles the chain kernel launches for a batch of utterances with these frame counts (every
+    utterance starts on a multiple of `align` frames of the global frame axis, gvn.engine.Batch)."""
+    return (sum((int(n) + align - 1) // align * align for n in n_frames) + tile - 1) // tile
+
+
+def wave_batches(n_frames, sms, waves=2, max_batch=256, align=32, tile=128):
+    """Cuts an ordered list of utterances (frame counts `n_frames`) into consecutive batches sized for the chain
+    kernel: one CTA per 128-frame tile, one CTA per SM, every tile of a launch takes the same time -- so a launch costs
+    ceil(tiles / sms) waves whatever the fill of its last wave.  A batch of 64 utterances of ~650 frames is 325 tiles =
+    2.2 waves on 148 SMs and pays for 3; here a batch takes as many utterances as fit `waves` full waves (at least one).
+    Returns a list of (start, stop) index pairs."""
+    budget = waves * sms * tile
+    out, start, used = [], 0, 0
+    for i, n in enumerate(n_frames):
+        a = (int(n) + align - 1) // align * align
+        if i > start and (used + a > budget or i - start >= max_batch):
+            out.append((start, i))
+            start, used = i, 0
+        used += a
+    if len(n_frames) > start:
+        out.append((start, len(n_frames)))
+    return out
+
+
 def gather_rows(rows, n_total, world=None, rank=None):
     """rows: (n_local, C) tensor of this rank's result rows (first column = utterance id).
     Returns the (n_total, C) table ordered by utterance id on every rank."""

@@ -22,6 +22,8 @@ Run from the repo root (the reference tree is read-only, so no bytecode is writt
   unmodified ``MCEM_M2`` with ``clean_speech_VAD`` labels, scored by the reference's ``python/metrics.py``.
 * ``spp_mask.npz`` -- ``timo_mask_estimation`` of ``python/models/spp_estimation.py`` on a synthetic mixture.
 * ``mcem_M2_noNMF.npz`` -- the same drive for ``MCEM_M2_noNMF`` (``mcem.py:609-760``).
+* ``labels.npz`` -- ``clean_speech_IBM`` / ``clean_speech_VAD`` of ``python/processing/target.py`` (imported unmodified) on
+  the complex64 STFT of a synthetic speech signal, at the scripts' quantile 0.999 and the functions' default 0.98.
 
 /root/reference does not exist on the GPU box; only the committed .npz files travel.
 """
@@ -316,8 +318,36 @@ def golden_spp():
     print("golden spp: %s frames, speech share %.3f" % (P.shape, float((mask > 0.5).mean())))
 
 
+def golden_labels(T=24000):
+    """clean_speech_IBM / clean_speech_VAD (python/processing/target.py:7-50) of the reference on a synthetic clean-speech
+    STFT (complex64, as evaluate_M2_ibm.py:115-123 feeds them).  The masks are discrete; the oracle must equal them exactly."""
+    sys.path.insert(0, REF)
+    for k in [k for k in sys.modules if k == "python" or k.startswith("python.")]:
+        del sys.modules[k]
+    from python.processing import target as ref_target
+    sys.path.remove(REF)
+    from oracle import mcem_oracle
+    _, s, _ = synth_utterance(5, seed=11, T=T)
+    S = stft_oracle.stft(s, **STFT_KW)
+    out = dict(S=S)
+    for q in (0.999, 0.98):
+        np.random.seed(0)                                   # target.py:17 draws (and discards) np.random.rand
+        ibm = ref_target.clean_speech_IBM(S, quantile_fraction=q, quantile_weight=0.999)
+        vad = ref_target.clean_speech_VAD(S, quantile_fraction=q, quantile_weight=0.999)
+        assert ibm.dtype == np.float32 and vad.dtype == np.float32 and vad.shape == (1, S.shape[1])
+        assert np.array_equal(mcem_oracle.clean_speech_IBM(S, q, 0.999), ibm)
+        assert np.array_equal(mcem_oracle.clean_speech_VAD(S, q, 0.999), vad)
+        out["ibm_%d" % round(q * 1000)] = ibm.astype(np.uint8)
+        out["vad_%d" % round(q * 1000)] = vad.astype(np.uint8)
+        print("golden labels q=%.3f: %s, speech share IBM %.4f VAD %.4f" % (q, S.shape, ibm.mean(), vad.mean()))
+    np.savez_compressed(os.path.join(OUT, "labels.npz"), **out)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if sys.argv[1:] == ["labels"]:
+        golden_labels()
+        sys.exit(0)
     golden_stft()
     golden_mcem("M1", "M1", None, L=16, K=4, niter=2, chain=(3, 4, 2, 5))
     golden_mcem("M2_ibm", "M2", "ibm", L=16, K=10, niter=3, chain=(3, 5, 4, 6))
@@ -325,3 +355,4 @@ if __name__ == "__main__":
     golden_nonmf()
     golden_spp()
     golden_real()
+    golden_labels()

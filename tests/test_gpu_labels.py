@@ -61,6 +61,16 @@ def test_mirror_functions_match_oracle(T):
     np.testing.assert_array_equal(clean_speech_VAD(S2, 0.98), O.clean_speech_VAD(S2, 0.98))
 
 
+@pytest.mark.parametrize("q", [0.999, 0.98])
+def test_mirror_functions_match_reference_golden(q):
+    """The drop-in module against masks the reference's own target.py produced (tests/golden/labels.npz)."""
+    import os
+    from python.processing.target import clean_speech_IBM, clean_speech_VAD
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "labels.npz"))
+    np.testing.assert_array_equal(clean_speech_IBM(z["S"], q, 0.999), z["ibm_%d" % round(q * 1000)])
+    np.testing.assert_array_equal(clean_speech_VAD(z["S"], q, 0.999), z["vad_%d" % round(q * 1000)])
+
+
 def test_enhancer_oracle_labels_on_device():
     """Enhancer(label_source='oracle_ibm'): clean speech in, STFT and labels on the device; equal to the oracle labels of
     the device's own clean-speech STFT, and the enhancement equals the one run with host-made labels."""

@@ -125,6 +125,43 @@ def test_enhance_many_equals_enhance():
             np.testing.assert_allclose(metrics[i], ref, rtol=1e-6, atol=1e-6)
 
 
+def test_enhance_many_over_a_ragged_list_with_device_labels():
+    """A file-list-like job: nine batches, every one with its own geometry (batch size AND lengths differ; more shapes than
+    the enhancer keeps batch state for), oracle labels made on the upload stream, two passes over the list.  The upload
+    thread allocates and drops memory while the compute stream is still working on the previous batches, so batch state
+    dropped by one stream must not be handed to the other early (this crashed with an illegal address when the label upload
+    shared full batch objects with the compute stream).  Results must equal the one-batch-at-a-time path exactly."""
+    from gvn.pipeline import McemConfig, Enhancer
+    from gvn.synth import synth_utterance
+    from python.models.models import DeepGenerativeModel
+    torch.manual_seed(0)
+    vae = DeepGenerativeModel([513, 513, 16, [128, 128]], None).eval()
+    cfg = McemConfig(model="M2", niter=2, nsamples_E_step=3, burnin_E_step=3, nsamples_WF=3, burnin_WF=3, nmf_rank=10, precision="f16")
+    enh = Enhancer(vae, cfg, "cuda:0", label_source="oracle_ibm")
+    rs = np.random.RandomState(3)
+    items = []
+    for k in range(9):
+        B = int(rs.randint(2, 9))
+        xs, ss, ns = zip(*[synth_utterance(10 * k + i, seed=6, T=256 * int(rs.randint(40, 140))) for i in range(B)])
+        items.append(dict(wavs=list(xs), refs=(list(ss), list(ns))))
+    assert len({tuple(len(w) for w in it["wavs"]) for it in items}) == 9
+    outs = []
+    for out in enh.enhance_many(items + items, seed=70):
+        outs.append((out["s_hat"].numpy().copy(), out["cost"].numpy().copy(), out["metrics"].numpy().copy(), list(out["T"])))
+    assert len(outs) == 18
+    for k, it in enumerate(items + items):
+        up = enh.upload(it["wavs"], refs=it["refs"])
+        b = enh.prepare(None, None, seed=70 + k, uploaded=up)
+        s_ref, _, cost_ref = enh.run(b, seed=70 + k)
+        torch.cuda.synchronize()
+        s_hat, cost, metrics, T = outs[k]
+        assert np.all(np.isfinite(cost)) and np.all(np.isfinite(metrics))
+        np.testing.assert_array_equal(cost, cost_ref.cpu().numpy())
+        s_ref = s_ref.cpu().numpy()
+        for i in range(len(it["wavs"])):
+            np.testing.assert_array_equal(s_hat[i, :T[i]], s_ref[i, :T[i]])
+
+
 @pytest.mark.parametrize("precision", ["fp32", "f16"])
 def test_real_wsj0_slice_matches_reference_golden(precision):
     """Real speech + noise from the reference's own fixture, enhanced by the unmodified reference (tests/golden/

@@ -126,3 +126,19 @@ def test_oracle_reproduces_reference_on_real_wsj0_slice():
     r = np.array(energy_ratios(s_hat.astype(np.float64), g["s"], g["n"]))
     np.testing.assert_allclose(r, g["ratios"], rtol=0, atol=1e-9)            # python/metrics.py of the reference
     assert r[0] > energy_ratios(g["x"], g["s"], g["n"])[0] + 2.0              # the enhancement does enhance (+3.1 dB SI-SDR)
+
+
+@pytest.mark.parametrize("q", [0.999, 0.98])
+def test_label_oracle_reproduces_reference_masks(q):
+    """tests/golden/labels.npz: clean_speech_IBM / clean_speech_VAD of the reference's python/processing/target.py:7-50 run
+    unmodified (oracle/make_golden.py golden_labels); discrete outputs, so exact.  Also the reference's own assertions
+    (tests/processing/test_target.py:49-50: float32, values {0, 1})."""
+    from oracle.mcem_oracle import clean_speech_IBM, clean_speech_VAD
+    z = np.load(os.path.join(GOLDEN, "labels.npz"))
+    S = z["S"]
+    assert S.dtype == np.complex64
+    ibm, vad = clean_speech_IBM(S, q, 0.999), clean_speech_VAD(S, q, 0.999)
+    assert ibm.dtype == np.float32 and np.unique(ibm).tolist() == [0.0, 1.0]
+    assert vad.dtype == np.float32 and vad.shape == (1, S.shape[1])
+    np.testing.assert_array_equal(ibm, z["ibm_%d" % round(q * 1000)])
+    np.testing.assert_array_equal(vad, z["vad_%d" % round(q * 1000)])

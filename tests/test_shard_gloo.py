@@ -6,7 +6,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from gvn.shard import shard_bounds, shard_list, gather_rows, length_sorted_shard
+from gvn.shard import shard_bounds, shard_list, gather_rows, length_sorted_shard, wave_batches, chain_tiles
 
 
 def test_shard_bounds_match_array_split():
@@ -18,6 +18,26 @@ def test_shard_bounds_match_array_split():
                 a, b = shard_bounds(n, world, r)
                 assert list(range(a, b)) == list(ref[r])
     assert shard_list(list("abcde"), 2, 0) == ["a", "b", "c"] and shard_list(list("abcde"), 2, 1) == ["d", "e"]
+
+
+def test_wave_batches_fill_whole_waves():
+    """Batches cut for the chain kernel (one 128-frame tile per SM and wave): consecutive, complete, never above the
+    budget of `waves` x 148 tiles unless a single utterance is, and fuller than fixed batches of 64."""
+    lens = np.random.RandomState(5).randint(537, 749, size=1024)
+    order = length_sorted_shard(lens, 1, 0)
+    n = [int(lens[i]) for i in order]
+    for waves in (1, 2, 4):
+        cuts = wave_batches(n, 148, waves)
+        assert cuts[0][0] == 0 and cuts[-1][1] == len(n) and all(a[1] == b[0] for a, b in zip(cuts, cuts[1:]))
+        tiles = [chain_tiles(n[a:b]) for a, b in cuts]
+        assert max(tiles) <= waves * 148 and min(tiles[:-1]) > waves * 148 - 8       # full up to one utterance (<= 6 tiles)
+        total = sum(-(-t // 148) for t in tiles)
+        fixed = sum(-(-chain_tiles(n[k:k + 64]) // 148) for k in range(0, len(n), 64))
+        assert total < fixed                                                          # 36 - 37 waves against 45
+    assert wave_batches([5000], 148, 1, align=32) == [(0, 1)]                         # a single over-long utterance still goes
+    assert wave_batches([], 148, 2) == []
+    assert wave_batches([100] * 10, 148, 2, max_batch=4) == [(0, 4), (4, 8), (8, 10)]
+    assert chain_tiles([251] * 64) == 128 and chain_tiles([1876] * 8) == 118
 
 
 def test_length_sorted_snake_shards_are_balanced():
