@@ -50,7 +50,7 @@ constexpr int NEW = NE / 32;            // epilogue warps
 constexpr int NTHREADS = 320;
 constexpr int STAGE_BYTES = SROWS * TM * 4;
 #ifndef GVN_TC_DEFAULT_VARIANT
-#define GVN_TC_DEFAULT_VARIANT 22
+#define GVN_TC_DEFAULT_VARIANT 86
 #endif
 
 // TMEM column map (512 columns allocated)
@@ -293,6 +293,53 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_estep_tc(const __grid_constant_
       fence_before();
     };
 
+    // V_SPLIT: the draw of a step takes ~3.4 k cycles on warps 4-7, the owners' accept + propose + first-layer wait only ~2 k
+    // -- the noise warps reach the first hidden layer late and the whole tile waits for their half of its columns (in-kernel
+    // counters: the owners wait 1.8 k cycles for the second layer's accumulator, the noise warps 0.4 k).  So only log u and
+    // the first two quads of eps are drawn at the start of the step; the other two quads follow where every epilogue warp
+    // idles anyway: while the first output chunk's MMA completes (nz_m carries the step number to that point of decode()).
+    constexpr bool V_SPLIT = PRE && (VAR & 64) != 0;
+    int nz_m = -1;
+    auto draw_quads = [&](int m, int lq0, uint32_t (&w)[8]) {     // quads lq0, lq0 + 1 of the noise of step m
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int lq = lq0 + j;
+        if (p.eps != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            w[4 * j + i] = __float_as_uint((4 * lq + i < L && in_range) ? p.eps[((size_t)m * L + 4 * lq + i) * NP + n] : 0.f);
+        } else {
+          uint4 rr = philox4x32_10(make_uint4((uint32_t)n, (uint32_t)m, (uint32_t)lq, (uint32_t)p.chain),
+                                   make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32)));
+          float2 a = box_muller(rr.x, rr.y), b = box_muller(rr.z, rr.w);
+          const float e4[4] = {a.x, a.y, b.x, b.y};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) w[4 * j + i] = __float_as_uint((4 * lq + i < L) ? e4[i] : 0.f);
+        }
+      }
+    };
+    auto stage_noise_a = [&](int m) {                 // warps 4-7: log u and eps[0..8) of step m -> TMEM
+      uint32_t w[8];
+      draw_quads(m, 0, w);
+      const float lu = draw_logu(m);
+      if (m >= 2) mbar_wait(bar_eps, (uint32_t)(m - 2) & 1);     // as in stage_noise
+      __syncwarp();
+      tmem_st8(tlane + COL_EPS + 16 * (m & 1), w);
+      tmem_st1(tlane + COL_LOGU + (m & 1), __float_as_uint(lu));
+      tmem_st_wait();
+      fence_before();
+      nz_m = m;
+    };
+    auto stage_noise_b = [&]() {                      // warps 4-7: eps[8..16) of step nz_m -> TMEM
+      uint32_t w[8];
+      draw_quads(nz_m, 2, w);
+      __syncwarp();
+      tmem_st8(tlane + COL_EPS + 16 * (nz_m & 1) + 8, w);
+      tmem_st_wait();
+      fence_before();
+      nz_m = -1;
+    };
+
     auto put_z = [&](const float (&zz)[L16]) {       // warps 0-3: Z operand (hi | lo) -> TMEM, signal the issuer
 #pragma unroll
       for (int k0 = 0; k0 < L16; k0 += 16) {
@@ -360,6 +407,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_estep_tc(const __grid_constant_
       constexpr bool ENERGY = decltype(energy_t)::value, STORE = decltype(store_t)::value;
       hidden(std::true_type{});
       hidden(std::false_type{});
+      if constexpr (V_SPLIT) { if (nz_m >= 0) stage_noise_b(); }     // under the wait for the first output chunk
       double dsum = 0.0;
       float* vo = STORE ? vs_out + tile_off(16 * half, n, F) : nullptr;   // column-tile order: bin stride = GVN_VS_TILE floats
 #pragma unroll 1
@@ -494,7 +542,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_estep_tc(const __grid_constant_
 
     // ---- chain ----
     if (half == 0) put_z(z);
-    if (PRE && half == 1 && n_steps > 0) stage_noise(0);
+    if (PRE && half == 1 && n_steps > 0) { if constexpr (V_SPLIT) stage_noise_a(0); else stage_noise(0); }
     Ct = decode(T, N, nullptr);
     int cur = 0;
     float cnt = 0.f;
@@ -519,14 +567,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_estep_tc(const __grid_constant_
         }
         float zq[L16];
 #pragma unroll
-        for (int l = 0; l < L16; ++l) { zq[l] = fmaf(p.sd, e[l], z[l]); prior += z[l] * z[l] - zq[l] * zq[l]; }
+        for (int l = 0; l < L16; ++l) zq[l] = fmaf(p.sd, e[l], z[l]);
         if (!PRE) {
 #pragma unroll
           for (int l = 0; l < L16; ++l) zp[l % (PRE ? 1 : L16)] = zq[l];
         }
-        put_z(zq);
+        put_z(zq);                                          // the issuer waits for this; the prior is not needed before the accept
+#pragma unroll
+        for (int l = 0; l < L16; ++l) prior += z[l] * z[l] - zq[l] * zq[l];
       } else if (PRE && m + 1 < n_steps) {
-        stage_noise(m + 1);
+        if constexpr (V_SPLIT) stage_noise_a(m + 1); else stage_noise(m + 1);
       }
       const int r = m - p.burnin;
       PROF(9);
@@ -659,7 +709,7 @@ int32_t launch_estep_tc(const gvn_batch* b, const void* packed, int burnin, int 
   a.prof = g_prof;
   const int grid = (b->NP + TM - 1) / TM;
   static int var = -1;                                  // GVN_TC_VARIANT: epilogue scheduling experiments (see `stage`)
-  if (var < 0) { const char* e = getenv("GVN_TC_VARIANT"); var = e ? atoi(e) & 31 : GVN_TC_DEFAULT_VARIANT; }
+  if (var < 0) { const char* e = getenv("GVN_TC_VARIANT"); var = e ? atoi(e) & 127 : GVN_TC_DEFAULT_VARIANT; }
   if (t.L16 == 16) {
     if (a.prof != nullptr) return launch_tc<16, true, GVN_TC_DEFAULT_VARIANT>(mx, a, grid, st);
     switch (var) {
@@ -667,6 +717,7 @@ int32_t launch_estep_tc(const gvn_batch* b, const void* packed, int burnin, int 
       case 3: return launch_tc<16, false, 3>(mx, a, grid, st);
       case 19: return launch_tc<16, false, 19>(mx, a, grid, st);
       case 23: return launch_tc<16, false, 23>(mx, a, grid, st);
+      case 22: return launch_tc<16, false, 22>(mx, a, grid, st);
       default: return launch_tc<16, false, GVN_TC_DEFAULT_VARIANT>(mx, a, grid, st);
     }
   }

@@ -28,6 +28,9 @@ for it in range(3):
     E.estep(b, enh.dec, 30, 10, 0.01, "f16", seed=1, chain=it)
 torch.cuda.synchronize()
 lib.gvn_debug_profile_buffer(C.c_void_p(buf.data_ptr()))
+E.estep(b, enh.dec, 30, 10, 0.01, "f16", seed=1, chain=5)             # first launch of the counting instantiation (attribute, load)
+torch.cuda.synchronize()
+buf.zero_()
 t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 t0.record()
 E.estep(b, enh.dec, 30, 10, 0.01, "f16", seed=1, chain=7)
