@@ -262,13 +262,25 @@ __global__ void __launch_bounds__(256) k_wiener(int F, int NP, int R, const int3
     float ws = 0.f, wn = 0.f;
     if (frame_utt[gn] >= 0) {
       const float gg = g[gn], vb = Vb[i];
-      for (int r = 0; r < R; ++r) {
-        const float w = Vs_w[(size_t)r * NP + gn];
-        if (w == 0.f) continue;                                 // dead slot (rejected proposal)
-        const float sc = gg * Vs[t + (size_t)r * slab];
-        const float wi = w * __frcp_rn(sc + vb);
-        ws = fmaf(wi, sc, ws);
-        wn = fmaf(wi, vb, wn);
+      // the slot reads are the traffic of this kernel (R x F x NP floats, read once): WU of them are requested before
+      // the first is used -- one load in flight per thread keeps ~8 KB per SM on the wire, a fifth of what the HBM latency needs
+      constexpr int WU = 5;
+      for (int r0 = 0; r0 < R; r0 += WU) {
+        float v[WU], w[WU];
+#pragma unroll
+        for (int u = 0; u < WU; ++u) {
+          const int r = r0 + u;
+          w[u] = r < R ? Vs_w[(size_t)r * NP + gn] : 0.f;
+          v[u] = r < R ? __ldcs(Vs + t + (size_t)r * slab) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < WU; ++u) {
+          if (w[u] == 0.f) continue;                            // dead slot (rejected proposal)
+          const float sc = gg * v[u];
+          const float wi = w[u] * __frcp_rn(sc + vb);
+          ws = fmaf(wi, sc, ws);
+          wn = fmaf(wi, vb, wn);
+        }
       }
       ws /= (float)R;
       wn /= (float)R;
