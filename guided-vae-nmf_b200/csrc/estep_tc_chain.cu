@@ -50,7 +50,7 @@ constexpr int NEW = NE / 32;            // epilogue warps
 constexpr int NTHREADS = 320;
 constexpr int STAGE_BYTES = SROWS * TM * 4;
 #ifndef GVN_TC_DEFAULT_VARIANT
-#define GVN_TC_DEFAULT_VARIANT 86
+#define GVN_TC_DEFAULT_VARIANT 84
 #endif
 
 // TMEM column map (512 columns allocated)
@@ -518,10 +518,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_estep_tc(const __grid_constant_
         };
         uint32_t ra[16], rb[16];
         if (V_PF) { tmem_ld16(tlane + acc_col, ra); tmem_ld_wait(); }
+        if constexpr (!V_PF && (VAR & 32) != 0) {            // one stage per loop iteration (half the code of the output loop)
 #pragma unroll 1
-        for (int s = 0; s < nst; s += 2) {
-          stage(ra, rb, s);
-          if (s + 1 < nst) stage(V_PF ? rb : ra, ra, s + 1);
+          for (int s = 0; s < nst; ++s) stage(ra, rb, s);
+        } else {
+#pragma unroll 1
+          for (int s = 0; s < nst; s += 2) {
+            stage(ra, rb, s);
+            if (s + 1 < nst) stage(V_PF ? rb : ra, ra, s + 1);
+          }
         }
         if (ENERGY) dsum += (double)fmaf(V_FRAC ? sl + (float)es : sl, LN2, sr);
         fence_before();
@@ -713,11 +718,9 @@ int32_t launch_estep_tc(const gvn_batch* b, const void* packed, int burnin, int 
   if (t.L16 == 16) {
     if (a.prof != nullptr) return launch_tc<16, true, GVN_TC_DEFAULT_VARIANT>(mx, a, grid, st);
     switch (var) {
-      case 0: return launch_tc<16, false, 0>(mx, a, grid, st);
-      case 3: return launch_tc<16, false, 3>(mx, a, grid, st);
-      case 19: return launch_tc<16, false, 19>(mx, a, grid, st);
-      case 23: return launch_tc<16, false, 23>(mx, a, grid, st);
       case 22: return launch_tc<16, false, 22>(mx, a, grid, st);
+      case 86: return launch_tc<16, false, 86>(mx, a, grid, st);
+      case 118: return launch_tc<16, false, 118>(mx, a, grid, st);
       default: return launch_tc<16, false, GVN_TC_DEFAULT_VARIANT>(mx, a, grid, st);
     }
   }
