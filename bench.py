@@ -144,6 +144,19 @@ def lib_hash():
         return None
 
 
+def src_hash():
+    """sha256 over the sources libgvn.so is built from (csrc/*.cu, *.cuh, the Makefile, include/gvn.h), in name order.
+    nvcc names the internal-linkage symbols of every compilation differently, so two builds of the same sources are not
+    byte-identical: the ncu capture is tied to this hash, the library's own sha256 is reported next to it."""
+    h = hashlib.sha256()
+    csrc = os.path.join(PKG, "csrc")
+    files = sorted(f for f in os.listdir(csrc) if f.endswith((".cu", ".cuh")) or f == "Makefile")
+    for f in [os.path.join(csrc, f) for f in files] + [os.path.join(ROOT, "include", "gvn.h")]:
+        h.update(os.path.basename(f).encode() + b"\0")
+        h.update(open(f, "rb").read())
+    return h.hexdigest()
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -607,8 +620,10 @@ def main():
     traffic, tr_note = {}, "no ncu capture of this build"
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")))
-        if tj.get("libgvn_sha256") == lib_hash() and tj.get("config") == args.config:
-            traffic, tr_note = tj, "profiles/r02_ncu_traffic.json (same libgvn.so sha256)"
+        same = tj.get("libgvn_sha256") == lib_hash() or tj.get("libgvn_src_sha256") == src_hash()
+        if same and tj.get("config") == args.config:
+            traffic, tr_note = tj, "profiles/r02_ncu_traffic.json (capture of a build of the same sources: %s)" % (
+                "same libgvn.so sha256" if tj.get("libgvn_sha256") == lib_hash() else "same source sha256")
         else:
             tr_note = "profiles/r02_ncu_traffic.json is from another build or workload (sha256 / config mismatch): not reported"
     except Exception:
@@ -625,7 +640,7 @@ def main():
             "quality": {"si_sdr_db_mean": float(rows[:, 1].mean()), "note": "random-init decoder (no trained weights ship with the "
                         "reference): the number checks plumbing, not enhancement quality"},
             "e2e": {"value": e2e_value, "unit": "utt/s", "h2d_bytes_per_step": int(h2d // args.steps), "d2h_bytes_per_step": int(d2h // args.steps)},
-            "gpu_launches": launches, "libgvn_sha256": lib_hash(),
+            "gpu_launches": launches, "libgvn_sha256": lib_hash(), "libgvn_src_sha256": src_hash(),
             "roofline": {"kernel": "gvn_estep (decoder MLP + MH chain, %s)" % args.precision, "bound": "tensor",
                          "achieved": e_tflops, "peak": tf_peak, "unit": "TFLOP/s", "frac": e_tflops / tf_peak,
                          "traffic": traffic.get("estep_bytes_per_launch"), "traffic_source": tr_note,
