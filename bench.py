@@ -157,6 +157,23 @@ def src_hash():
     return h.hexdigest()
 
 
+def ncu_traffic(config, precision, path=None):
+    """DRAM bytes per launch of the two hot kernels from the committed `ncu --set full` capture -- reported only when the
+    capture was made on a build of THESE sources (binary or source sha256), for this workload and this chain arithmetic.
+    Returns (dict or {}, note)."""
+    path = path or os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")
+    try:
+        tj = json.load(open(path))
+    except Exception:
+        return {}, "no ncu capture of this build"
+    same_bin = tj.get("libgvn_sha256") is not None and tj.get("libgvn_sha256") == lib_hash()
+    same_src = tj.get("libgvn_src_sha256") is not None and tj.get("libgvn_src_sha256") == src_hash()
+    if (same_bin or same_src) and tj.get("config") == config and tj.get("precision", "f16") == precision:
+        return tj, "%s (capture of a build of the same sources: %s)" % (
+            os.path.relpath(path, ROOT), "same libgvn.so sha256" if same_bin else "same source sha256")
+    return {}, "%s is from another build or workload (sha256 / config / precision mismatch): not reported" % os.path.relpath(path, ROOT)
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -617,17 +634,7 @@ def main():
     m_gbs = nmf_bytes / (m_ms_tot * 1e-3) / 1e9
     # DRAM traffic per launch of the two hot kernels from the committed `ncu --set full` capture (profiles/): only
     # reported when the capture was made with THIS build of libgvn.so and this workload
-    traffic, tr_note = {}, "no ncu capture of this build"
-    try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")))
-        same = tj.get("libgvn_sha256") == lib_hash() or tj.get("libgvn_src_sha256") == src_hash()
-        if same and tj.get("config") == args.config:
-            traffic, tr_note = tj, "profiles/r02_ncu_traffic.json (capture of a build of the same sources: %s)" % (
-                "same libgvn.so sha256" if tj.get("libgvn_sha256") == lib_hash() else "same source sha256")
-        else:
-            tr_note = "profiles/r02_ncu_traffic.json is from another build or workload (sha256 / config mismatch): not reported"
-    except Exception:
-        pass
+    traffic, tr_note = ncu_traffic(args.config, args.precision)
     n_e = timers.count("estep")
 
     if rank == 0:

@@ -127,3 +127,27 @@ def test_staging_buffers_grow_instead_of_accumulating():
     for k in range(200):                                   # 200 distinct shapes: still one buffer
         engine._grow_view(cache, "wav", (7, 100 + k), make)
     assert len(cache) == 1 and cache["wav"].numel() < 2 * 7 * 300
+
+
+def test_bench_reports_ncu_traffic_only_for_the_same_build(tmp_path):
+    """bench.py copies the DRAM traffic of the committed ncu capture into `roofline.traffic` only when the capture was
+    made on a build of the same sources (binary or source sha256), for the same workload and chain arithmetic."""
+    import json
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    h = bench.src_hash()
+    assert h == bench.src_hash() and len(h) == 64
+    p = tmp_path / "traffic.json"
+    rec = dict(libgvn_sha256="0" * 64, libgvn_src_sha256=h, config="C2", precision="f16", estep_bytes_per_launch=1, mstep_bytes_per_launch=2)
+    p.write_text(json.dumps(rec))
+    t, note = bench.ncu_traffic("C2", "f16", str(p))
+    assert t["estep_bytes_per_launch"] == 1 and "same source sha256" in note
+    for cfg, prec in (("C4", "f16"), ("C2", "fp32")):
+        t, note = bench.ncu_traffic(cfg, prec, str(p))
+        assert t == {} and "not reported" in note
+    rec["libgvn_src_sha256"] = "1" * 64
+    p.write_text(json.dumps(rec))
+    t, note = bench.ncu_traffic("C2", "f16", str(p))
+    assert t == {} and "not reported" in note
+    assert bench.ncu_traffic("C2", "f16", str(tmp_path / "missing.json"))[0] == {}
