@@ -65,3 +65,30 @@ def test_rejects_garbage(tmp_path):
     open(p, "wb").write(b"not a wav file at all")
     with pytest.raises(ValueError):
         wavio.read(p)
+
+
+@pytest.mark.parametrize("subtype", ["PCM_16", "FLOAT"])
+def test_cross_check_with_scipy_wavfile(tmp_path, subtype):
+    """A second, independent RIFF implementation (scipy.io.wavfile): files written here are read by scipy sample for sample,
+    and files written by scipy (int16, int32, float32, stereo) come back from `read` with libsndfile's scaling (int / 2^(bits-1))."""
+    wavfile = pytest.importorskip("scipy.io.wavfile")
+    rs = np.random.RandomState(4)
+    x = np.clip(0.3 * rs.randn(4001), -1.0, 1.0)
+    p = str(tmp_path / "a.wav")
+    wavio.write(p, x, 16000, subtype=subtype)
+    fs, y = wavfile.read(p)
+    assert fs == 16000 and y.shape == (4001,)
+    if subtype == "PCM_16":
+        assert y.dtype == np.int16
+        np.testing.assert_array_equal(y, wavio.pcm16(x))
+    else:
+        assert y.dtype == np.float32
+        np.testing.assert_array_equal(y, x.astype(np.float32))
+    for arr, scale in ((rs.randint(-32768, 32768, size=(3000, 2)).astype(np.int16), 32768.0),
+                       (rs.randint(-2 ** 31, 2 ** 31 - 1, size=2999).astype(np.int32), 2147483648.0),
+                       (rs.randn(1234).astype(np.float32), 1.0)):
+        q = str(tmp_path / "b.wav")
+        wavfile.write(q, 8000, arr)
+        z, fs = wavio.read(q)
+        assert fs == 8000 and z.shape == arr.shape and z.dtype == np.float64
+        np.testing.assert_array_equal(z, arr.astype(np.float64) / scale)
