@@ -25,6 +25,12 @@ Run from the repo root (the reference tree is read-only, so no bytecode is writt
 * ``labels.npz`` -- ``clean_speech_IBM`` / ``clean_speech_VAD`` of ``python/processing/target.py`` (imported unmodified) on
   the complex64 STFT of a synthetic speech signal, at the scripts' quantile 0.999 and the functions' default 0.98.
 
+* ``labels_wsj0.npz`` -- the reference's OWN committed label fixtures (``data/subset/pickle/CSR-1-WSJ-0/si_dt_05_labels.p``,
+  ``si_dt_05_vad_labels.p``: ``clean_speech_IBM`` / ``clean_speech_VAD`` at quantile 0.98 per utterance, written by
+  ``tests/dataset/test_csr1_wjs0_dataset.py``) next to the power spectrograms they were made from (``si_dt_05_frames.p``) and
+  the utterance boundaries, which the fixture does not store: they are recovered here as the one segmentation under which the
+  restated rule reproduces every one of the 513 x 976 labels.
+
 /root/reference does not exist on the GPU box; only the committed .npz files travel.
 """
 import os
@@ -343,10 +349,42 @@ def golden_labels(T=24000):
     np.savez_compressed(os.path.join(OUT, "labels.npz"), **out)
 
 
+def golden_label_fixture(name="si_dt_05"):
+    """The reference's committed label pickles against its committed power spectrograms (see the module docstring)."""
+    import itertools
+    import pickle
+    from oracle.mcem_oracle import lorenz_mask
+
+    class NumpyOnly(pickle.Unpickler):                      # the pickles are untrusted input: numpy reconstruction only
+        def find_class(self, module, cls):
+            if module.split(".")[0] == "numpy":
+                return super().find_class(module, cls)
+            raise pickle.UnpicklingError("blocked %s.%s" % (module, cls))
+
+    base = os.path.join(REF, "data", "subset", "pickle", "CSR-1-WSJ-0")
+    load = lambda suffix: NumpyOnly(open(os.path.join(base, "%s_%s.p" % (name, suffix)), "rb")).load()
+    P, ibm, vad = load("frames"), load("labels"), load("vad_labels")
+    assert P.dtype == np.float32 and P.shape == ibm.shape and vad.shape == (1, P.shape[1])
+    N = P.shape[1]
+    # three utterances per subset: the first boundary is where a prefix reproduces its labels, the second where a suffix does
+    first = [b for b in range(50, N - 50) if np.array_equal(lorenz_mask(P[:, :b], 0.98), ibm[:, :b])]
+    last = [a for a in range(50, N - 50) if np.array_equal(lorenz_mask(P[:, a:], 0.98), ibm[:, a:])]
+    found = [(b1, b2) for b1, b2 in itertools.product(first, last) if b1 < b2 and
+             np.array_equal(lorenz_mask(P[:, b1:b2], 0.98), ibm[:, b1:b2])]
+    assert len(found) == 1, found
+    bounds = np.array([0, found[0][0], found[0][1], N], np.int32)
+    for a, b in zip(bounds[:-1], bounds[1:]):
+        assert np.array_equal(lorenz_mask(P[:, a:b].sum(axis=0), 0.98)[None], vad[:, a:b])
+    np.savez_compressed(os.path.join(OUT, "labels_wsj0.npz"), power=P, ibm=np.packbits(ibm.astype(np.uint8), axis=1),
+                        vad=vad.astype(np.uint8), bounds=bounds)
+    print("golden label fixture %s: %s, utterances at %s, speech share IBM %.4f VAD %.4f" % (name, P.shape, bounds, ibm.mean(), vad.mean()))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     if sys.argv[1:] == ["labels"]:
         golden_labels()
+        golden_label_fixture()
         sys.exit(0)
     golden_stft()
     golden_mcem("M1", "M1", None, L=16, K=4, niter=2, chain=(3, 4, 2, 5))
@@ -356,3 +394,4 @@ if __name__ == "__main__":
     golden_spp()
     golden_real()
     golden_labels()
+    golden_label_fixture()

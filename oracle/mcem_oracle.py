@@ -311,24 +311,24 @@ class McemNoNmfOracle(McemOracle):
 # ----------------------------------------------------------------------------------------
 # labels and metric (small, so kept with the oracle)
 # ----------------------------------------------------------------------------------------
-def clean_speech_IBM(S, quantile_fraction=0.98, quantile_weight=0.999):
-    """processing/target.py:7-27 -- Lorenz-curve threshold on the clean-speech power."""
-    power = np.abs(S * S.conj())
+def lorenz_mask(power, quantile_fraction=0.98, quantile_weight=0.999):
+    """The threshold rule both label functions of processing/target.py share (:18-26, :41-49), on a power array of any shape:
+    sort descending, cumulative share (Lorenz curve), threshold = last value whose share is below `quantile_fraction`,
+    mask = power > threshold, softened by `quantile_weight` and rounded back to {0, 1}."""
     srt = np.sort(power, axis=None)[::-1]
     lorenz = np.cumsum(srt) / np.sum(srt)
     thr = srt[lorenz < quantile_fraction][-1]
-    mask = np.round(0.5 + quantile_weight * ((power > thr) - 0.5))
-    return np.float32(mask)
+    return np.float32(np.round(0.5 + quantile_weight * ((power > thr) - 0.5)))
+
+
+def clean_speech_IBM(S, quantile_fraction=0.98, quantile_weight=0.999):
+    """processing/target.py:7-27 -- Lorenz-curve threshold on the clean-speech power."""
+    return lorenz_mask(np.abs(S * S.conj()), quantile_fraction, quantile_weight)
 
 
 def clean_speech_VAD(S, quantile_fraction=0.98, quantile_weight=0.999):
     """processing/target.py:29-50 -- same on the per-frame summed power; returns (1,N)."""
-    power = np.abs(S * S.conj()).sum(axis=0)
-    srt = np.sort(power, axis=None)[::-1]
-    lorenz = np.cumsum(srt) / np.sum(srt)
-    thr = srt[lorenz < quantile_fraction][-1]
-    vad = np.round(0.5 + quantile_weight * ((power > thr) - 0.5))
-    return np.float32(vad)[None]
+    return lorenz_mask(np.abs(S * S.conj()).sum(axis=0), quantile_fraction, quantile_weight)[None]
 
 
 def energy_ratios(s_hat, s, n):

@@ -107,3 +107,22 @@ def test_argument_checks():
     for qf, qw in ((0.0, 0.999), (1.5, 0.999), (0.98, 0.0), (0.98, 1.5)):
         with pytest.raises(_lib.GvnError):
             E.speech_labels(b, S, False, qf, qw)
+
+
+@pytest.mark.parametrize("vad", [False, True])
+def test_device_labels_reproduce_the_references_own_label_fixture(vad):
+    """gvn_speech_labels on the reference's committed power spectrograms (three WSJ0 utterances as one ragged batch) against the
+    reference's committed label pickles (tests/golden/labels_wsj0.npz, see tests/test_oracle_golden.py): every label equal."""
+    import os
+    from gvn import engine as E
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "labels_wsj0.npz"))
+    P, bounds = z["power"], z["bounds"]
+    ref = z["vad"].astype(np.float32) if vad else np.unpackbits(z["ibm"], axis=1)[:, :P.shape[1]].astype(np.float32)
+    b = E.Batch([int(n) for n in np.diff(bounds)], 513, 1, 1, 1, "cuda:0", with_complex=False)
+    Pd = torch.full((513, b.NP), float("nan"), device="cuda")
+    for i, (a, c) in enumerate(zip(bounds[:-1], bounds[1:])):
+        Pd[:, b.cols(i)] = torch.from_numpy(P[:, a:c]).cuda()
+    y = E.speech_labels(b, Pd, vad, 0.98, 0.999, from_power=True)
+    torch.cuda.synchronize()
+    for i, (a, c) in enumerate(zip(bounds[:-1], bounds[1:])):
+        np.testing.assert_array_equal(y[:, b.cols(i)].cpu().numpy(), ref[:, a:c])

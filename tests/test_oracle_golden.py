@@ -142,3 +142,21 @@ def test_label_oracle_reproduces_reference_masks(q):
     assert vad.dtype == np.float32 and vad.shape == (1, S.shape[1])
     np.testing.assert_array_equal(ibm, z["ibm_%d" % round(q * 1000)])
     np.testing.assert_array_equal(vad, z["vad_%d" % round(q * 1000)])
+
+
+def test_label_oracle_reproduces_the_references_own_label_fixture():
+    """tests/golden/labels_wsj0.npz: the reference's COMMITTED label pickles (data/subset/pickle/CSR-1-WSJ-0/si_dt_05_labels.p and
+    si_dt_05_vad_labels.p, written by its tests/dataset/test_csr1_wjs0_dataset.py with clean_speech_IBM / clean_speech_VAD at
+    quantile 0.98) next to the power spectrograms they were made from (si_dt_05_frames.p): three WSJ0 utterances, 513 x 976 bins.
+    The threshold rule of the oracle reproduces every label, per utterance."""
+    from oracle.mcem_oracle import lorenz_mask
+    z = np.load(os.path.join(GOLDEN, "labels_wsj0.npz"))
+    P, bounds = z["power"], z["bounds"]
+    ibm = np.unpackbits(z["ibm"], axis=1)[:, :P.shape[1]].astype(np.float32)
+    vad = z["vad"].astype(np.float32)
+    assert P.shape == (513, 976) and bounds.tolist() == [0, 341, 640, 976] and 0.05 < ibm.mean() < 0.15
+    for a, b in zip(bounds[:-1], bounds[1:]):
+        np.testing.assert_array_equal(lorenz_mask(P[:, a:b], 0.98, 0.999), ibm[:, a:b])
+        np.testing.assert_array_equal(lorenz_mask(P[:, a:b].sum(axis=0), 0.98, 0.999)[None], vad[:, a:b])
+    # the rule is per utterance: over the concatenation it gives different labels
+    assert not np.array_equal(lorenz_mask(P, 0.98, 0.999), ibm)
