@@ -1,2 +1,2 @@
 # times the compiled scheduling variants of the chain kernel (GVN_TC_VARIANT) at the benchmark shape
-for v in ${@:-86 84 118 116 112 116 84}; do echo "variant $v"; GVN_TC_VARIANT=$v python tools/estep_time.py; done
+for v in ${@:-84 86 118 22 84}; do echo "variant $v"; GVN_TC_VARIANT=$v python tools/estep_time.py; done
